@@ -1,0 +1,132 @@
+// Shared device/host helpers for the b2k kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/b2k.h"
+
+namespace b2k {
+
+constexpr int kList = B2K_LIST;  // entries per (query, split) partial list
+
+// ---------------------------------------------------------------------------------------
+// error plumbing (api.cu owns the thread-local message)
+void set_error(const char* fmt, ...);
+
+#define B2K_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      b2k::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+      return (int)e_;                                                                    \
+    }                                                                                    \
+  } while (0)
+
+#define B2K_CHECK_LAUNCH() B2K_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------
+// (score, row) records.  Partial lists and candidate buffers are arrays of these.
+struct __align__(8) Cand {
+  float score;
+  int32_t row;  // local row in the shard, -1 = empty
+};
+
+// Total order used everywhere: higher score first, then lower row/offset.  Mapped to one
+// uint64 so that "better" == numerically larger.  NaN scores sort last.
+__host__ __device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t b;
+#ifdef __CUDA_ARCH__
+  b = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } v; v.f = f; b = v.u;
+#endif
+  if ((b & 0x7fffffffu) > 0x7f800000u) return 0u;       // NaN -> worst
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ uint64_t cand_key(float score, int32_t row) {
+  // empty slots (row < 0) get key 0: below every real entry
+  if (row < 0) return 0ull;
+  return ((uint64_t)float_key(score) << 32) | (uint32_t)(0x7fffffff - row);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+  uint32_t k = (uint32_t)(key >> 32);
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  union { float f; uint32_t u; } v; v.u = b; return v.f;
+#endif
+}
+__host__ __device__ __forceinline__ int32_t key_row(uint64_t key) {
+  return key == 0ull ? -1 : (int32_t)(0x7fffffff - (uint32_t)(key & 0xffffffffu));
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// Arithmetic specs shared bit-for-bit with oracle/b2k_oracle.c.
+//
+// sumsq32 / dot64: element i of a vector belongs to lane (i/4) % 32; each lane folds its
+// elements in increasing i with one FMA each; lanes are combined by the xor butterfly
+// 16,8,4,2,1 (a+b is commutative, so every lane ends with identical bits).
+
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Lane-partial Σ x_i² over x[0..d) following the spec (vector loads when 16B-aligned).
+__device__ __forceinline__ float lane_sumsq(const float* __restrict__ x, int d, int lane) {
+  float p = 0.f;
+  const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int c = lane; c < (d >> 2); c += 32) {
+      float4 v = x4[c];
+      p = __fmaf_rn(v.x, v.x, p); p = __fmaf_rn(v.y, v.y, p);
+      p = __fmaf_rn(v.z, v.z, p); p = __fmaf_rn(v.w, v.w, p);
+    }
+  } else {
+    for (int c = lane; c * 4 < d; c += 32) {
+      for (int j = 0; j < 4; ++j) {
+        int i = c * 4 + j;
+        if (i < d) { float v = x[i]; p = __fmaf_rn(v, v, p); }
+      }
+    }
+  }
+  return p;
+}
+
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t h) {
+  return __uint_as_float(((uint32_t)h) << 16);
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------
+// Synthetic generator (Spec G) — integer hashing + exact int->float steps only, so that
+// oracle/synth.py reproduces every bit on the CPU.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// Irwin–Hall(4) of 16-bit uniforms, unit variance.
+__host__ __device__ __forceinline__ float gauss4(uint64_t h) {
+  int32_t a = (int32_t)(h & 0xffff) + (int32_t)((h >> 16) & 0xffff) +
+              (int32_t)((h >> 32) & 0xffff) + (int32_t)(h >> 48);
+  return (float)(a - 131070) * (1.0f / 37837.8f);
+}
+
+}  // namespace b2k

@@ -1,0 +1,152 @@
+// Host-visible launch wrappers and argument blocks of the b2k kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace b2k {
+
+struct PackArgs {
+  const float* tables[B2K_MAX_TABLES];  // device [n, d_t]
+  int32_t dims[B2K_MAX_TABLES];
+  int32_t col_off[B2K_MAX_TABLES];
+  int32_t n_tables;
+  int32_t D, Dp;
+  int32_t normalize;      // 1: per-table L2 normalise (build); 0: copy/convert only (load)
+  int64_t n;              // rows in this call
+  int64_t row0;           // first output row
+  float* out_f32;         // [cap, D]   (may be null)
+  uint16_t* out_bf16;     // [cap, Dp]  (may be null)
+  float* out_norm2;       // [cap]      (may be null)
+  unsigned int* stat_bits;  // [0] max ||bf16(y)-y||² bits, [1] max ||y||² bits (may be null)
+};
+
+struct QueryPrepArgs {
+  const float* q;       // [nq, D]
+  uint16_t* q_bf16;     // [nq_pad, Dp]
+  float* qn2;           // [nq]
+  float* eps_scan;      // [nq]
+  float* eps_tc;        // [nq]
+  const unsigned int* stat_bits;
+  float acc_rel;
+  int32_t nq, nq_pad, D, Dp;
+};
+
+struct SynthArgs {
+  float* tables[B2K_MAX_TABLES];
+  int32_t dims[B2K_MAX_TABLES];
+  int32_t n_tables;
+  int32_t query_mode;
+  int64_t n, first, total_rows;
+  uint64_t seed, qseed;
+  int32_t n_clusters;
+  uint32_t abs_mask;
+  float sigma, sigma_q;
+};
+
+struct ScanArgs {
+  const uint16_t* db;   // bf16 [n_rows, Dp]
+  int64_t n_rows;
+  int32_t D, Dp;
+  const float* q;       // fp32 [nq, D]
+  int32_t nq;           // total queries
+  int32_t q0;           // first query of this pass
+  int32_t n_splits;     // == gridDim.x
+  Cand* partial;        // [nq, n_splits, kList]
+};
+
+struct SelectArgs {
+  const Cand* partial;  // [nq, n_splits, kList]
+  int32_t n_splits;
+  int32_t n_rerank;     // C'
+  int32_t* cand_rows;   // [nq, C']
+  float* thr;           // [nq]
+};
+
+struct RerankArgs {
+  const float* db_f32;  // [n_rows, D]
+  const float* q;       // [nq, D]
+  const int32_t* cand_rows;  // [nq, C']
+  float* cand_ip;       // [nq, C']
+  int32_t nq, n_rerank, D;
+};
+
+struct FinalizeArgs {
+  const int32_t* cand_rows;
+  const float* cand_ip;
+  const float* thr;
+  const float* eps;       // per query slack of the path that produced the candidates
+  const float* qn2;
+  const float* norm2;     // per DB row
+  int32_t nq, n_rerank, k;
+  int64_t base_offset;
+  int32_t force_exact;
+  float* out_ip;          // [nq, k] (may be null)
+  float* out_dist;        // [nq, k]
+  int64_t* out_labels;    // [nq, k]
+  int32_t* fail_count;    // [1]
+  int32_t* fail_list;     // [nq]
+  float* eps_max_bits;    // [1] (as uint bits)
+};
+
+struct ExactArgs {
+  const float* db_f32;
+  const float* norm2;
+  int64_t n_rows;
+  int32_t D;
+  const float* q;
+  const float* qn2;
+  int32_t nq, k;
+  int64_t base_offset;
+  const int32_t* fail_count;
+  const int32_t* fail_list;
+  Cand* partial;          // [max_fail_slots, n_splits, kList] exact scores
+  int32_t n_splits;
+  float* out_ip; float* out_dist; int64_t* out_labels;
+};
+
+struct MergeArgs {
+  const float* ip; const float* dist; const int64_t* labels;  // [n_lists, nq, k]
+  int32_t n_lists, nq, k;
+  float* out_ip; float* out_dist; int64_t* out_labels;        // [nq, k]
+};
+
+int launch_pack(const PackArgs& a, cudaStream_t st);
+int launch_normalize(float* x, int64_t n, int d, cudaStream_t st);
+int launch_query_prep(const QueryPrepArgs& a, cudaStream_t st);
+int launch_synth(const SynthArgs& a, cudaStream_t st);
+
+// K-scan: returns the number of splits it will use for a device with n_sm SMs.
+int scan_num_splits(int n_sm);
+bool scan_supports(int Dp);
+int launch_scan(const ScanArgs& a, int n_queries_this_pass, cudaStream_t st);
+
+int launch_select(const SelectArgs& a, int nq, cudaStream_t st);
+int launch_rerank(const RerankArgs& a, cudaStream_t st);
+int launch_finalize(const FinalizeArgs& a, cudaStream_t st);
+int exact_num_splits(int n_sm);
+int launch_exact(const ExactArgs& a, cudaStream_t st);   // scan + finalize of failed queries
+int launch_merge(const MergeArgs& a, cudaStream_t st);
+
+// K-score (tcgen05): see score_tc.cu
+struct ScoreTcPlan {
+  int32_t n_qtiles;     // query tiles of 128
+  int32_t n_splits;     // DB splits per query tile
+  int32_t grid;         // CTAs
+};
+struct ScoreTcArgs {
+  const void* tmap_q;   // CUtensorMap* (host copy passed by value at launch)
+  const void* tmap_db;
+  int64_t n_rows;
+  int32_t Dp;
+  int32_t nq;
+  ScoreTcPlan plan;
+  Cand* partial;        // [nq, n_splits, kList]
+};
+bool score_tc_supports(int Dp);
+ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits);
+int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_bf16, int nq_pad,
+                         const uint16_t* db_bf16, int64_t n_rows, int Dp);
+int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st);
+
+}  // namespace b2k

@@ -1,0 +1,402 @@
+// K-scan: small-batch (nq <= 4 per pass) approximate scoring of the whole bf16 shard on the
+// CUDA cores, HBM-bound by construction.  Replaces the inner loop of
+// index.search(query_vec, top_k) (main/search_from_image.py:247) for tiny query batches
+// (the reference is always batch-1).
+//
+// Layout: one persistent CTA per SM owns a contiguous row range (split).  A producer thread
+// streams 8-row slabs (contiguous bytes) into a shared-memory ring with 1-D bulk async
+// copies (UBLKCP) completing on mbarriers; 8 consumer warps read the slab with conflict-free
+// 16-byte LDS, multiply against the fp32 query held in registers, and reduce 32 (row,query)
+// sums per step with a transposed warp butterfly (31 shuffles for 32 values).  The running
+// top-32 per (query, split) lives in shared memory, one entry per lane of warp 0, guarded by a
+// threshold so inserts become rare.  Only 32 records per (query, split) ever reach HBM.
+//
+// Also here: K-exact, the fp32/fp64 exhaustive scan serving queries whose certificate failed.
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b2k {
+
+namespace {
+constexpr int kScanRowsPerStage = 8;
+constexpr int kScanConsumers = 256;
+constexpr int kScanThreads = kScanConsumers + 32;
+constexpr int kScanSmemBudget = 200 * 1024;
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint64_t u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = u < v ? u : v;
+  }
+  return v;
+}
+
+// Insert (s,row) into the lane-per-entry list `lst` (shared, 32 Cands) if it beats the
+// current minimum; returns the new threshold (min score when the list is full, else -inf).
+__device__ __forceinline__ float warp_list_insert(Cand* lst, int lane, float s, int32_t row) {
+  Cand e = lst[lane];
+  // (key, lane) so that exactly one lane owns the minimum even among empty slots
+  uint64_t k = cand_key(e.score, e.row);
+  uint64_t kl = (k & ~31ull) | (uint64_t)lane;  // low 5 bits of the row field are irrelevant for min-pick
+  // Using the masked key only to pick a victim; exact comparison below uses full keys.
+  uint64_t kmin = warp_min_u64(kl);
+  // among candidates whose masked key equals the min prefix choose by full key then lane
+  bool is_victim = (kl == kmin);
+  if (is_victim) { e.score = s; e.row = row; lst[lane] = e; }
+  __syncwarp();
+  // new threshold
+  float sc = e.row < 0 ? -INFINITY : e.score;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sc = fminf(sc, __shfl_xor_sync(0xffffffffu, sc, o));
+  return sc;
+}
+}  // namespace
+
+template <int NQ, int CH>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_bf16_kernel(ScanArgs a, int n_stages, int stage_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* ring = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
+  uint64_t* empty = full + n_stages;
+  float* red = reinterpret_cast<float*>(empty + n_stages);      // [2][8][32]
+  Cand* lists = reinterpret_cast<Cand*>(red + 2 * 8 * 32);      // [NQ][32]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int64_t r_begin = a.n_rows * (int64_t)split / a.n_splits;
+  const int64_t r_end = a.n_rows * (int64_t)(split + 1) / a.n_splits;
+  const int64_t n_local = r_end - r_begin;
+  const int n_iter = (int)((n_local + kScanRowsPerStage - 1) / kScanRowsPerStage);
+  const int row_bytes = a.Dp * 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 8); }
+    ptx::fence_mbar_init();
+  }
+  if (tid < NQ * 32) { lists[tid].score = -INFINITY; lists[tid].row = -1; }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % n_stages;
+        if (it >= n_stages) ptx::mbar_wait(&empty[s], ((it / n_stages) - 1) & 1);
+        const int64_t r0 = r_begin + (int64_t)it * kScanRowsPerStage;
+        const int nr = (int)min((int64_t)kScanRowsPerStage, r_end - r0);
+        const uint32_t bytes = (uint32_t)nr * row_bytes;
+        ptx::mbar_arrive_expect_tx(&full[s], bytes);
+        ptx::bulk_g2s(ring + (size_t)s * stage_bytes, a.db + r0 * a.Dp, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
+  const int n_chunks = a.Dp >> 3;
+  // query registers: chunk tid (+256 for CH==2), 8 floats per query
+  float qr[CH][NQ][8];
+#pragma unroll
+  for (int m = 0; m < CH; ++m) {
+    const int c = tid + m * kScanConsumers;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = c * 8 + j;
+        const int qi = a.q0 + q;
+        qr[m][q][j] = (c < n_chunks && col < a.D && qi < a.nq) ? a.q[(int64_t)qi * a.D + col] : 0.f;
+      }
+  }
+
+  constexpr int kRowsPerGroup = 32 / NQ;                       // rows per reduction
+  constexpr int kSubs = kRowsPerGroup / kScanRowsPerStage;     // stages per reduction
+  static_assert(kSubs >= 1, "NQ too large");
+  float tau[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) tau[q] = -INFINITY;
+
+  int it = 0;
+  int buf = 0;
+  for (int64_t g0 = 0; g0 < n_local; g0 += kRowsPerGroup) {
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int sub = 0; sub < kSubs; ++sub) {
+      if (it < n_iter) {
+        const int s = it % n_stages;
+        ptx::mbar_wait(&full[s], (it / n_stages) & 1);
+        const unsigned char* slab = ring + (size_t)s * stage_bytes;
+#pragma unroll
+        for (int m = 0; m < CH; ++m) {
+          const int c = tid + m * kScanConsumers;
+          if (c < n_chunks) {
+            uint4 v[kScanRowsPerStage];
+#pragma unroll
+            for (int r = 0; r < kScanRowsPerStage; ++r)
+              v[r] = *reinterpret_cast<const uint4*>(slab + (size_t)r * row_bytes + (size_t)c * 16);
+#pragma unroll
+            for (int r = 0; r < kScanRowsPerStage; ++r) {
+              float x[8];
+              x[0] = __uint_as_float(v[r].x << 16); x[1] = __uint_as_float(v[r].x & 0xffff0000u);
+              x[2] = __uint_as_float(v[r].y << 16); x[3] = __uint_as_float(v[r].y & 0xffff0000u);
+              x[4] = __uint_as_float(v[r].z << 16); x[5] = __uint_as_float(v[r].z & 0xffff0000u);
+              x[6] = __uint_as_float(v[r].w << 16); x[7] = __uint_as_float(v[r].w & 0xffff0000u);
+#pragma unroll
+              for (int q = 0; q < NQ; ++q) {
+                float s2 = acc[(sub * kScanRowsPerStage + r) * NQ + q];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s2 = fmaf(x[j], qr[m][q][j], s2);
+                acc[(sub * kScanRowsPerStage + r) * NQ + q] = s2;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        ++it;
+      }
+    }
+    // transposed butterfly: afterwards lane L holds Σ_lanes acc[L]
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const float send = upper ? acc[i] : acc[i + o];
+        const float keep = upper ? acc[i + o] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    red[(buf * 8 + warp) * 32 + lane] = acc[0];
+    ptx::named_bar_sync(1, kScanConsumers);
+    if (warp == 0) {
+      float sc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sc += red[(buf * 8 + w) * 32 + lane];
+      const int rr = lane / NQ, qq = lane % NQ;
+      const int64_t lrow = g0 + rr;                      // row within the split
+      const int32_t row = (int32_t)(r_begin + lrow);
+      float my_tau = tau[0];
+#pragma unroll
+      for (int q = 1; q < NQ; ++q) my_tau = (qq == q) ? tau[q] : my_tau;
+      bool want = (lrow < n_local) && (a.q0 + qq < a.nq) && (sc > my_tau);
+      unsigned m = __ballot_sync(0xffffffffu, want);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        const float s_in = __shfl_sync(0xffffffffu, sc, src);
+        const int32_t r_in = __shfl_sync(0xffffffffu, row, src);
+        const int q_in = src % NQ;
+        const float nt = warp_list_insert(lists + q_in * 32, lane, s_in, r_in);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) if (q == q_in) tau[q] = nt;
+        if (lane == src) want = false;
+        if (qq == q_in) want = want && (sc > nt);
+        m = __ballot_sync(0xffffffffu, want);
+      }
+    }
+    buf ^= 1;
+  }
+
+  // all consumers must be past their last red[] read before exit is irrelevant; only warp 0
+  // touches the lists, so it can write them out directly.
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int qi = a.q0 + q;
+      if (qi < a.nq) a.partial[((int64_t)qi * a.n_splits + split) * kList + lane] = lists[q * 32 + lane];
+    }
+  }
+}
+
+int scan_num_splits(int n_sm) { return n_sm; }
+bool scan_supports(int Dp) { return Dp >= 8 && (Dp % 8) == 0 && Dp <= 2 * kScanConsumers * 8; }
+
+template <int NQ, int CH>
+static int launch_scan_t(const ScanArgs& a, cudaStream_t st) {
+  const int stage_bytes = kScanRowsPerStage * a.Dp * 2;
+  const int fixed = 2 * 8 * 32 * 4 + NQ * 32 * (int)sizeof(Cand) + 256;
+  int n_stages = (kScanSmemBudget - fixed) / (stage_bytes + 16);
+  if (n_stages > 8) n_stages = 8;
+  if (n_stages < 2) { set_error("scan: Dp=%d does not fit the shared-memory ring", a.Dp); return B2K_E_INVALID; }
+  const size_t smem = (size_t)n_stages * stage_bytes + (size_t)n_stages * 16 + fixed;
+  auto kern = scan_bf16_kernel<NQ, CH>;
+  B2K_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<a.n_splits, kScanThreads, smem, st>>>(a, n_stages, stage_bytes);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_scan(const ScanArgs& a, int nq_pass, cudaStream_t st) {
+  if (!scan_supports(a.Dp)) { set_error("scan: unsupported Dp=%d", a.Dp); return B2K_E_INVALID; }
+  const bool ch2 = (a.Dp >> 3) > kScanConsumers;
+  if (nq_pass <= 1) return ch2 ? launch_scan_t<1, 2>(a, st) : launch_scan_t<1, 1>(a, st);
+  if (nq_pass <= 2) return ch2 ? launch_scan_t<2, 2>(a, st) : launch_scan_t<2, 1>(a, st);
+  if (nq_pass <= 4) return ch2 ? launch_scan_t<4, 2>(a, st) : launch_scan_t<4, 1>(a, st);
+  set_error("scan: at most 4 queries per pass (got %d)", nq_pass);
+  return B2K_E_INVALID;
+}
+
+// =========================================================================================
+// K-exact: exhaustive fp32 scan with fp64 accumulation (Spec R) for uncertified queries.
+// One warp per row, up to 4 failed queries per sweep, warp-private top-32 in registers
+// (one entry per lane), merged per CTA at the end.  Launched unconditionally; exits at once
+// when fail_count == 0, so no host synchronisation is needed to decide.
+namespace {
+constexpr int kExactFQ = 4;
+constexpr int kExactWarps = 8;
+
+__device__ __forceinline__ void block_bitonic_desc(uint64_t* keys, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool desc = (i & k) == 0;
+          const uint64_t x = keys[i], y = keys[ixj];
+          if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kExactWarps * 32)
+exact_scan_kernel(ExactArgs a) {
+  __shared__ uint64_t keys[kExactFQ][kExactWarps * 32];
+  const int n_fail = *a.fail_count;
+  if (n_fail == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * kExactWarps + warp;
+  const int64_t nw = (int64_t)gridDim.x * kExactWarps;
+  const bool vec = ((a.D & 3) == 0);
+  for (int f0 = 0; f0 < n_fail; f0 += kExactFQ) {
+    const float* qp[kExactFQ];
+    float e_s[kExactFQ]; int32_t e_r[kExactFQ]; float tau[kExactFQ];
+#pragma unroll
+    for (int f = 0; f < kExactFQ; ++f) {
+      const int fi = f0 + f < n_fail ? f0 + f : n_fail - 1;   // duplicates are harmless
+      qp[f] = a.q + (int64_t)a.fail_list[fi] * a.D;
+      e_s[f] = -INFINITY; e_r[f] = -1; tau[f] = -INFINITY;
+    }
+    for (int64_t row = gw; row < a.n_rows; row += nw) {
+      const float* x = a.db_f32 + row * (int64_t)a.D;
+      double p[kExactFQ];
+#pragma unroll
+      for (int f = 0; f < kExactFQ; ++f) p[f] = 0.0;
+      if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        for (int c = lane; c < (a.D >> 2); c += 32) {
+          const float4 v = x4[c];
+#pragma unroll
+          for (int f = 0; f < kExactFQ; ++f) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(qp[f]) + c);
+            p[f] = __fma_rn((double)w.x, (double)v.x, p[f]);
+            p[f] = __fma_rn((double)w.y, (double)v.y, p[f]);
+            p[f] = __fma_rn((double)w.z, (double)v.z, p[f]);
+            p[f] = __fma_rn((double)w.w, (double)v.w, p[f]);
+          }
+        }
+      } else {
+        for (int c = lane; c * 4 < a.D; c += 32)
+          for (int j = 0; j < 4; ++j) {
+            const int i = c * 4 + j;
+            if (i < a.D) {
+              const double v = (double)x[i];
+#pragma unroll
+              for (int f = 0; f < kExactFQ; ++f) p[f] = __fma_rn((double)__ldg(qp[f] + i), v, p[f]);
+            }
+          }
+      }
+#pragma unroll
+      for (int f = 0; f < kExactFQ; ++f) {
+        const float ip = (float)warp_sum_f64(p[f]);
+        if (ip > tau[f] || (ip == tau[f] && false)) {
+          // replace the warp list's minimum (lane-per-entry, in registers)
+          const uint64_t k = cand_key(e_s[f], e_r[f]);
+          const uint64_t kl = (k & ~31ull) | (uint64_t)lane;
+          uint64_t kmin = kl;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t u = __shfl_xor_sync(0xffffffffu, kmin, o);
+            kmin = u < kmin ? u : kmin;
+          }
+          if (kl == kmin) { e_s[f] = ip; e_r[f] = (int32_t)row; }
+          float sc = e_r[f] < 0 ? -INFINITY : e_s[f];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sc = fminf(sc, __shfl_xor_sync(0xffffffffu, sc, o));
+          tau[f] = sc;
+        }
+      }
+    }
+    // CTA merge of the 8 warp lists -> top-32 per failed query
+#pragma unroll
+    for (int f = 0; f < kExactFQ; ++f) keys[f][threadIdx.x] = cand_key(e_s[f], e_r[f]);
+    __syncthreads();
+    for (int f = 0; f < kExactFQ; ++f) {
+      block_bitonic_desc(keys[f], kExactWarps * 32);
+      if (f0 + f < n_fail && threadIdx.x < kList) {
+        Cand c; const uint64_t k = keys[f][threadIdx.x];
+        c.score = key_score(k); c.row = key_row(k);
+        if (c.row < 0) c.score = -INFINITY;
+        a.partial[((int64_t)(f0 + f) * a.n_splits + blockIdx.x) * kList + threadIdx.x] = c;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// One CTA per failed query: sort n_splits*32 exact records, emit the top-k.
+__global__ void __launch_bounds__(512)
+exact_finalize_kernel(ExactArgs a, int P) {
+  extern __shared__ uint64_t skeys[];
+  const int n_fail = *a.fail_count;
+  const int f = blockIdx.x;
+  if (f >= n_fail) return;
+  const int q = a.fail_list[f];
+  const int M = a.n_splits * kList;
+  const Cand* src = a.partial + (int64_t)f * M;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    uint64_t k = 0;
+    if (i < M) { const Cand c = src[i]; k = cand_key(c.score, c.row); }
+    skeys[i] = k;
+  }
+  __syncthreads();
+  block_bitonic_desc(skeys, P);
+  if (threadIdx.x < a.k) {
+    const int j = threadIdx.x;
+    const uint64_t k = skeys[j];
+    const int32_t row = key_row(k);
+    float ip = -3.402823466e38f, dist = 3.402823466e38f; int64_t lab = -1;
+    if (row >= 0) {
+      ip = key_score(k);
+      lab = a.base_offset + row;
+      dist = fmaxf(__fmaf_rn(-2.0f, ip, __fadd_rn(a.qn2[q], a.norm2[row])), 0.f);
+    }
+    if (a.out_ip) a.out_ip[(int64_t)q * a.k + j] = ip;
+    a.out_dist[(int64_t)q * a.k + j] = dist;
+    a.out_labels[(int64_t)q * a.k + j] = lab;
+  }
+}
+
+int exact_num_splits(int n_sm) { return 2 * n_sm; }
+
+int launch_exact(const ExactArgs& a, cudaStream_t st) {
+  exact_scan_kernel<<<a.n_splits, kExactWarps * 32, 0, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  int P = 1; while (P < a.n_splits * kList) P <<= 1;
+  const size_t smem = (size_t)P * 8;
+  B2K_CUDA(cudaFuncSetAttribute(exact_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  exact_finalize_kernel<<<a.nq, 512, smem, st>>>(a, P);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace b2k

@@ -1,0 +1,140 @@
+/*
+ * b2k.h — C ABI of the B200-native exact top-k engine behind the image_recommender
+ * retrieval hot path.
+ *
+ * The reference (AAPPHH/image_recommender) has no FFI layer of its own; its boundary to
+ * native arithmetic is the faiss Python object protocol.  Every entry point below names
+ * the reference call site (path:line under /root/reference) it replaces.  All functions
+ * are called from ONE host thread per index; the library owns all device memory; host
+ * pointers are borrowed only for the duration of a call.  No torch types appear here.
+ *
+ * Status convention: 0 = ok, >0 = cudaError_t, <0 = B2K_E_* below.  After any non-zero
+ * status b2k_last_error() returns a thread-local human-readable message.
+ *
+ * There is deliberately NO CPU implementation behind this ABI: without a CUDA device
+ * every compute entry point returns an error.
+ */
+#ifndef B2K_H_
+#define B2K_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2K_ABI_VERSION 1
+#define B2K_MAX_TABLES 8
+#define B2K_MAX_K 32          /* top-k limit of the fused selection (list width per DB split) */
+#define B2K_LIST 32           /* entries kept per (query, DB split) by the scoring kernels   */
+
+#define B2K_E_INVALID  (-1)   /* bad argument                                   */
+#define B2K_E_CAPACITY (-2)   /* add() beyond the capacity given to create()    */
+#define B2K_E_IO       (-3)   /* save/load failure                              */
+#define B2K_E_NODEVICE (-4)   /* no CUDA device / wrong architecture            */
+#define B2K_E_NOMEM    (-5)   /* host allocation failure                        */
+
+typedef struct b2k_index b2k_index;
+
+/* b2k_set_option keys */
+#define B2K_OPT_PATH          1  /* 0 auto, 1 = K-scan (CUDA-core stream), 2 = K-score (tcgen05 GEMM) */
+#define B2K_OPT_RERANK        2  /* candidates re-ranked in fp32 per query (C'), 32..1024, default 64   */
+#define B2K_OPT_FORCE_EXACT   3  /* 1 = treat every query as uncertified (exercise the exact fp32 scan) */
+#define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 4)    */
+#define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
+
+typedef struct b2k_stats {
+  int32_t path;            /* 1 = K-scan, 2 = K-score for the last search                    */
+  int32_t n_splits;        /* DB splits (partial lists) per query                            */
+  int32_t n_rerank;        /* C' used                                                        */
+  int32_t n_uncertified;   /* queries whose certificate failed -> served by exact fp32 scan  */
+  float   eps_max;         /* largest certificate slack used (bound on |bf16 score - exact|) */
+  float   err_max;         /* max_row ||bf16(x) - x||_2 over the shard                       */
+  float   norm_max;        /* max_row ||x||_2 over the shard                                 */
+  int32_t launches;        /* kernels launched by the last search                            */
+} b2k_stats;
+
+typedef struct b2k_synth {
+  uint64_t seed;
+  int32_t  n_clusters;     /* image-level clusters shared by all tables (default 4096) */
+  float    sigma;          /* intra-cluster noise scale (default 0.3)                  */
+  uint32_t abs_mask;       /* bit t set: table t is non-negative (colour histograms)   */
+  int64_t  total_rows;     /* N of the whole (all-shard) DB; queries draw rows from it  */
+} b2k_synth;
+
+const char* b2k_last_error(void);
+int32_t     b2k_abi_version(void);
+int         b2k_device_count(int32_t* n);
+
+/* Replaces faiss.IndexHNSWFlat(dim, M) / IndexIVFPQ(...) construction
+ * (main/create_index.py:207-234).  One flat exact store per GPU shard.
+ * table_dims[t] = d_t in concat order; rows get global offsets base_offset + local row. */
+int b2k_create(const int32_t* table_dims, int32_t n_tables, int64_t capacity_rows,
+               int32_t device, int64_t base_offset, b2k_index** out);
+void b2k_destroy(b2k_index* idx);
+
+/* Replaces index.add(arr) (main/create_index.py:311) fused with the per-row
+ * np.concatenate of _process_batch (main/create_index.py:176-188): host_tables[t] is a
+ * C-contiguous fp32 [n, d_t] host array; rows are per-table L2-normalised, concatenated,
+ * stored as fp32 and bf16.  Row i gets offset base_offset + ntotal_before + i. */
+int b2k_add(b2k_index* idx, const float* const* host_tables, int64_t n);
+/* Same with device-resident inputs on `stream` (cudaStream_t as void*). */
+int b2k_add_device(b2k_index* idx, const float* const* dev_tables, int64_t n, void* stream);
+
+/* index.ntotal (main/create_index.py:321, main/search_from_image.py:340) */
+int64_t b2k_ntotal(const b2k_index* idx);
+int32_t b2k_dim(const b2k_index* idx);
+int32_t b2k_dim_padded(const b2k_index* idx);
+int64_t b2k_base_offset(const b2k_index* idx);
+
+/* Replaces index.search(query_vec, top_k) (main/search_from_image.py:247).
+ * q: fp32 [nq, D] host.  Outputs (host): dist fp32 [nq,k] squared-L2 (ascending when all
+ * rows share one norm, as per-table normalisation guarantees), labels int64 [nq,k] global
+ * offsets, -1 padded when k > ntotal (faiss convention).  ip (optional, may be NULL)
+ * receives the exact fp32 inner products, descending. */
+int b2k_search(b2k_index* idx, const float* q_host, int32_t nq, int32_t k,
+               float* dist_host, int64_t* labels_host, float* ip_host);
+/* Device-resident variant: q_dev/outputs are device pointers, work is enqueued on
+ * `stream` and NOT synchronised. */
+int b2k_search_device(b2k_index* idx, const float* q_dev, int32_t nq, int32_t k,
+                      float* dist_dev, int64_t* labels_dev, float* ip_dev, void* stream);
+int b2k_get_stats(b2k_index* idx, b2k_stats* out);   /* synchronises the last search */
+int b2k_set_option(b2k_index* idx, int32_t key, int64_t value);
+
+/* Cross-shard merge (new): n_lists per-shard results [n_lists, nq, k] ->
+ * [nq, k], order = higher ip first, then lower offset.  All pointers on `device`. */
+int b2k_merge_topk_device(const float* ip, const float* dist, const int64_t* labels,
+                          int32_t n_lists, int32_t nq, int32_t k,
+                          float* out_ip, float* out_dist, int64_t* out_labels,
+                          int32_t device, void* stream);
+
+/* Replaces faiss.normalize_L2(x) (main/search_from_image.py:322): in place on a host
+ * array, rows with zero norm untouched; computed on `device`. */
+int b2k_normalize_l2(float* x_host, int64_t n, int32_t d, int32_t device);
+
+/* Replace faiss.write_index / faiss.read_index (main/create_index.py:320,
+ * main/search_from_image.py:339).  ids (optional) = image_id per row, carried in the file.
+ * load() reads rows [row_begin, row_end) of the file (row_end < 0: to the end) so that
+ * each GPU of a row-sharded deployment loads only its shard. */
+int b2k_save(b2k_index* idx, const char* path, const int64_t* ids, int64_t n_ids);
+int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_end,
+             b2k_index** out);
+int b2k_file_info(const char* path, int64_t* n_rows, int32_t* n_tables, int32_t* table_dims,
+                  int32_t* has_ids);
+int b2k_load_ids(const char* path, int64_t row_begin, int64_t n, int64_t* ids_out);
+
+/* Read back packed rows (parity tests): any of the outputs may be NULL. */
+int b2k_get_rows(b2k_index* idx, int64_t row0, int64_t n, float* f32_host,
+                 uint16_t* bf16_host, float* norm2_host);
+
+/* Device-side synthetic data for benches: appends n clustered rows whose
+ * global offsets start at base_offset + ntotal; bit-reproducible on the CPU
+ * (oracle/synth.py).  Queries are noisy copies of seeded DB rows, whole-vector normalised. */
+int b2k_fill_synthetic(b2k_index* idx, int64_t n, const b2k_synth* p);
+int b2k_synth_queries_device(b2k_index* idx, int32_t nq, const b2k_synth* p, uint64_t qseed,
+                             float sigma_q, float* q_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2K_H_ */
