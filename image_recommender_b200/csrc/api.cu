@@ -1,0 +1,751 @@
+// C ABI of the b2k engine (include/b2k.h): index object, build (add), search pipeline,
+// persistence and the synthetic-data helpers.  Host side only; kernels live in pack.cu,
+// scan.cu, score_tc.cu and select.cu.
+#include <cuda.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2k {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+constexpr int64_t kStageRows = 16384;     // rows per host->device staging chunk of add()/load()
+constexpr int kMaxNqPerPass = 16384;      // queries per pipeline pass (workspace sizing)
+constexpr int kDefaultCandCap = 1024;
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  B2K_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return 0;
+}
+template <typename T>
+void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+struct Workspace {
+  int nq_cap = 0, n_lists = 0, cand_cap = 0, exact_splits = 0;
+  float* q = nullptr;             // [nq, D] staging for the host API
+  uint16_t* q_bf16 = nullptr;     // [nq_pad, Dp]
+  float *qn2 = nullptr, *eps_scan = nullptr, *eps_tc = nullptr, *thr = nullptr;
+  Cand* partial = nullptr;        // [nq, n_lists, 32]
+  int32_t *cand_rows = nullptr, *cand_count = nullptr, *flags = nullptr;
+  float* cand_ip = nullptr;
+  int32_t *fail_count = nullptr, *fail_list = nullptr;
+  Cand* exact_partial = nullptr;  // [nq, exact_splits, 32]
+  float *out_ip = nullptr, *out_dist = nullptr;
+  int64_t* out_labels = nullptr;
+  void release() {
+    dev_free(q); dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr);
+    dev_free(partial); dev_free(cand_rows); dev_free(cand_count); dev_free(flags); dev_free(cand_ip);
+    dev_free(fail_count); dev_free(fail_list); dev_free(exact_partial);
+    dev_free(out_ip); dev_free(out_dist); dev_free(out_labels);
+    nq_cap = 0;
+  }
+};
+
+}  // namespace
+}  // namespace b2k
+
+using namespace b2k;
+
+struct b2k_index {
+  int device = 0, n_sm = 0;
+  int n_tables = 0;
+  int32_t dims[B2K_MAX_TABLES] = {0}, col_off[B2K_MAX_TABLES] = {0};
+  int32_t D = 0, Dp = 0;
+  int64_t cap = 0, ntotal = 0, base = 0;
+  float* f32 = nullptr;
+  uint16_t* bf16 = nullptr;
+  float* norm2 = nullptr;
+  unsigned int* stat_bits = nullptr;
+  cudaStream_t stream = nullptr;
+  float* stage[B2K_MAX_TABLES] = {nullptr};   // device staging of raw per-table rows
+  float* stage_rows_f32 = nullptr;            // device staging of packed rows (load)
+  Workspace ws;
+  // TMA descriptors (host copies; passed by value at launch)
+  alignas(64) CUtensorMap tmap_q, tmap_db;
+  const void* tmap_q_ptr = nullptr; int tmap_q_rows = 0;
+  const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
+  // options
+  int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 4, opt_splits = 0;
+  b2k_stats stats;
+  int32_t* h_fail = nullptr;                  // pinned
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // before scoring, after scoring, after the tail
+  bool ev_valid = false;
+};
+
+namespace {
+
+int make_col_offsets(b2k_index* ix) {
+  int off = 0;
+  for (int t = 0; t < ix->n_tables; ++t) { ix->col_off[t] = off; off += ix->dims[t]; }
+  ix->D = off;
+  ix->Dp = (off + 63) / 64 * 64;
+  return 0;
+}
+
+int ensure_stage(b2k_index* ix) {
+  for (int t = 0; t < ix->n_tables; ++t)
+    if (!ix->stage[t]) { int rc = dev_alloc(&ix->stage[t], (size_t)kStageRows * ix->dims[t]); if (rc) return rc; }
+  return 0;
+}
+
+void fill_pack_args(const b2k_index* ix, PackArgs& a, int64_t n, int64_t row0, int normalize) {
+  memset(&a, 0, sizeof(a));
+  a.n_tables = ix->n_tables;
+  for (int t = 0; t < ix->n_tables; ++t) {
+    a.dims[t] = ix->dims[t]; a.strides[t] = ix->dims[t]; a.col_off[t] = ix->col_off[t];
+  }
+  a.D = ix->D; a.Dp = ix->Dp; a.normalize = normalize; a.n = n; a.row0 = row0;
+  a.out_f32 = ix->f32; a.out_bf16 = ix->bf16; a.out_norm2 = ix->norm2; a.stat_bits = ix->stat_bits;
+}
+
+int ensure_workspace(b2k_index* ix, int nq) {
+  Workspace& w = ix->ws;
+  const int scan_lists = scan_num_splits(ix->n_sm);
+  const int tc_lists = ix->n_sm;
+  const int n_lists = std::max(scan_lists, tc_lists);
+  const int exact_splits = exact_num_splits(ix->n_sm);
+  if (nq <= w.nq_cap && w.n_lists == n_lists && w.cand_cap == ix->opt_cand_cap) return 0;
+  B2K_CUDA(cudaStreamSynchronize(ix->stream));
+  w.release();
+  const int cap = std::max(nq, 8);
+  const int nq_pad = (cap + 127) / 128 * 128;
+  int rc = 0;
+  if ((rc = dev_alloc(&w.q, (size_t)cap * ix->D))) return rc;
+  if ((rc = dev_alloc(&w.q_bf16, (size_t)nq_pad * ix->Dp))) return rc;
+  if ((rc = dev_alloc(&w.qn2, cap))) return rc;
+  if ((rc = dev_alloc(&w.eps_scan, cap))) return rc;
+  if ((rc = dev_alloc(&w.eps_tc, cap))) return rc;
+  if ((rc = dev_alloc(&w.thr, cap))) return rc;
+  if ((rc = dev_alloc(&w.partial, (size_t)cap * n_lists * kList))) return rc;
+  if ((rc = dev_alloc(&w.cand_rows, (size_t)cap * ix->opt_cand_cap))) return rc;
+  if ((rc = dev_alloc(&w.cand_ip, (size_t)cap * ix->opt_cand_cap))) return rc;
+  if ((rc = dev_alloc(&w.cand_count, cap))) return rc;
+  if ((rc = dev_alloc(&w.flags, cap))) return rc;
+  if ((rc = dev_alloc(&w.fail_count, 1))) return rc;
+  if ((rc = dev_alloc(&w.fail_list, cap))) return rc;
+  if ((rc = dev_alloc(&w.exact_partial, (size_t)cap * exact_splits * kList))) return rc;
+  if ((rc = dev_alloc(&w.out_ip, (size_t)cap * B2K_MAX_K))) return rc;
+  if ((rc = dev_alloc(&w.out_dist, (size_t)cap * B2K_MAX_K))) return rc;
+  if ((rc = dev_alloc(&w.out_labels, (size_t)cap * B2K_MAX_K))) return rc;
+  w.nq_cap = cap; w.n_lists = n_lists; w.cand_cap = ix->opt_cand_cap; w.exact_splits = exact_splits;
+  ix->tmap_q_ptr = nullptr;   // q_bf16 moved
+  return 0;
+}
+
+// One pass of the search pipeline over nq <= ws.nq_cap device-resident queries.
+int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_dev, int64_t* labels_dev,
+                float* ip_dev, cudaStream_t st) {
+  Workspace& w = ix->ws;
+  int launches = 0;
+  const int nq_pad = (nq + 127) / 128 * 128;
+
+  QueryPrepArgs qp;
+  qp.q = q_dev; qp.q_bf16 = w.q_bf16; qp.qn2 = w.qn2; qp.eps_scan = w.eps_scan; qp.eps_tc = w.eps_tc;
+  qp.stat_bits = ix->stat_bits;
+  qp.nq = nq; qp.nq_pad = nq_pad; qp.D = ix->D; qp.Dp = ix->Dp;
+  int rc = launch_query_prep(qp, st);
+  if (rc) return rc;
+  ++launches;
+  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, sizeof(int32_t), st));
+
+  // ---- path selection
+  int path = ix->opt_path;
+  if (path == 0) path = (nq <= ix->opt_scan_max_b && scan_supports(ix->Dp)) ? 1 : 2;
+  if (path == 2 && (!score_tc_supports(ix->Dp) || ix->ntotal == 0)) path = 1;
+  if (path == 1 && !scan_supports(ix->Dp)) { set_error("no scoring path supports Dp=%d", ix->Dp); return B2K_E_INVALID; }
+
+  int n_lists_used = 0;
+  const float* eps = nullptr;
+  B2K_CUDA(cudaEventRecord(ix->ev[0], st));
+  if (path == 1) {
+    ScanArgs sa;
+    sa.db = ix->bf16; sa.n_rows = ix->ntotal; sa.D = ix->D; sa.Dp = ix->Dp; sa.q = q_dev; sa.nq = nq;
+    sa.n_splits = scan_num_splits(ix->n_sm); sa.partial = w.partial; sa.n_lists = w.n_lists;
+    for (int q0 = 0; q0 < nq; q0 += 4) {
+      sa.q0 = q0;
+      rc = launch_scan(sa, std::min(4, nq - q0), st);
+      if (rc) return rc;
+      ++launches;
+    }
+    n_lists_used = sa.n_splits;
+    eps = w.eps_scan;
+  } else {
+    if (ix->tmap_db_ptr != ix->bf16 || ix->tmap_db_rows != ix->ntotal) {
+      rc = score_tc_encode_maps(nullptr, &ix->tmap_db, nullptr, 0, ix->bf16, ix->ntotal, ix->Dp);
+      if (rc) return rc;
+      ix->tmap_db_ptr = ix->bf16; ix->tmap_db_rows = ix->ntotal;
+    }
+    if (ix->tmap_q_ptr != w.q_bf16 || ix->tmap_q_rows != nq_pad) {
+      rc = score_tc_encode_maps(&ix->tmap_q, nullptr, w.q_bf16, nq_pad, nullptr, 0, ix->Dp);
+      if (rc) return rc;
+      ix->tmap_q_ptr = w.q_bf16; ix->tmap_q_rows = nq_pad;
+    }
+    ScoreTcArgs ta;
+    ta.tmap_q = &ix->tmap_q; ta.tmap_db = &ix->tmap_db; ta.n_rows = ix->ntotal; ta.Dp = ix->Dp; ta.nq = nq;
+    ta.plan = score_tc_plan(nq, ix->ntotal, ix->n_sm, std::min(ix->opt_splits, w.n_lists));
+    ta.partial = w.partial; ta.n_lists = w.n_lists;
+    rc = launch_score_tc(ta, st);
+    if (rc) return rc;
+    ++launches;
+    n_lists_used = ta.plan.n_splits;
+    eps = w.eps_tc;
+  }
+  B2K_CUDA(cudaEventRecord(ix->ev[1], st));
+  // the select kernel reads lists [0, n_lists_used) of the stride-n_lists layout
+  SelectArgs se;
+  se.partial = w.partial; se.n_lists = n_lists_used; se.list_stride = w.n_lists; se.k = k; se.eps = eps;
+  se.cand_cap = w.cand_cap; se.force_exact = ix->opt_force_exact;
+  se.cand_rows = w.cand_rows; se.cand_count = w.cand_count; se.flags = w.flags; se.thr = w.thr;
+  rc = launch_select(se, nq, st);
+  if (rc) return rc;
+  ++launches;
+
+  RerankArgs rr;
+  rr.db_f32 = ix->f32; rr.q = q_dev; rr.cand_rows = w.cand_rows; rr.cand_count = w.cand_count;
+  rr.cand_ip = w.cand_ip; rr.nq = nq; rr.cand_cap = w.cand_cap; rr.D = ix->D;
+  rc = launch_rerank(rr, ix->n_sm, st);
+  if (rc) return rc;
+  ++launches;
+
+  FinalizeArgs fa;
+  fa.cand_rows = w.cand_rows; fa.cand_count = w.cand_count; fa.cand_ip = w.cand_ip; fa.flags = w.flags;
+  fa.qn2 = w.qn2; fa.norm2 = ix->norm2; fa.nq = nq; fa.cand_cap = w.cand_cap; fa.k = k;
+  fa.base_offset = ix->base; fa.out_ip = ip_dev; fa.out_dist = dist_dev; fa.out_labels = labels_dev;
+  fa.fail_count = w.fail_count; fa.fail_list = w.fail_list;
+  rc = launch_finalize(fa, st);
+  if (rc) return rc;
+  ++launches;
+
+  ExactArgs ea;
+  ea.db_f32 = ix->f32; ea.norm2 = ix->norm2; ea.n_rows = ix->ntotal; ea.D = ix->D; ea.q = q_dev;
+  ea.qn2 = w.qn2; ea.nq = nq; ea.k = k; ea.base_offset = ix->base; ea.fail_count = w.fail_count;
+  ea.fail_list = w.fail_list; ea.partial = w.exact_partial; ea.n_splits = w.exact_splits;
+  ea.out_ip = ip_dev; ea.out_dist = dist_dev; ea.out_labels = labels_dev;
+  rc = launch_exact(ea, st);
+  if (rc) return rc;
+  launches += 2;
+  B2K_CUDA(cudaEventRecord(ix->ev[2], st));
+  ix->ev_valid = true;
+
+  ix->stats.path = path;
+  ix->stats.n_uncertified = -1;      // on the device until read back
+  ix->stats.n_splits = n_lists_used;
+  ix->stats.n_rerank = w.cand_cap;
+  ix->stats.launches = launches;
+  return 0;
+}
+
+int check_search_args(const b2k_index* ix, const void* q, int nq, int k, const void* dist, const void* labels) {
+  if (!ix || !q || !dist || !labels || nq <= 0 || k <= 0) { set_error("search: bad argument"); return B2K_E_INVALID; }
+  if (k > B2K_MAX_K) { set_error("search: k=%d exceeds B2K_MAX_K=%d", k, B2K_MAX_K); return B2K_E_INVALID; }
+  return 0;
+}
+
+// ---- file format -------------------------------------------------------------------------
+struct FileHeader {
+  char magic[8];            // "B2KIDX01"
+  int32_t version, n_tables;
+  int32_t dims[B2K_MAX_TABLES];
+  int32_t D, has_ids;
+  int64_t n_rows;
+  int64_t rows_offset, ids_offset;
+  char pad[48];
+};
+static_assert(sizeof(FileHeader) == 128, "header layout");
+
+int read_header(FILE* f, FileHeader& h, const char* path) {
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "B2KIDX01", 8) != 0 || h.version != 1 ||
+      h.n_tables < 1 || h.n_tables > B2K_MAX_TABLES) {
+    set_error("%s: not a b2k index file", path);
+    return B2K_E_IO;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* b2k_last_error(void) { return g_err; }
+int32_t b2k_abi_version(void) { return B2K_ABI_VERSION; }
+
+int b2k_device_count(int32_t* n) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *n = 0; set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return B2K_E_NODEVICE; }
+  *n = c;
+  return 0;
+}
+
+int b2k_create(const int32_t* table_dims, int32_t n_tables, int64_t capacity_rows, int32_t device,
+               int64_t base_offset, b2k_index** out) {
+  if (!out) { set_error("create: out is null"); return B2K_E_INVALID; }
+  *out = nullptr;
+  if (!table_dims || n_tables < 1 || n_tables > B2K_MAX_TABLES || capacity_rows < 0 ||
+      capacity_rows > 0x7fffff00ll) {
+    set_error("create: bad argument (n_tables=%d capacity=%lld)", n_tables, (long long)capacity_rows);
+    return B2K_E_INVALID;
+  }
+  for (int t = 0; t < n_tables; ++t)
+    if (table_dims[t] < 1) { set_error("create: table %d has dim %d", t, table_dims[t]); return B2K_E_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("create: no CUDA device (this engine has no CPU path)");
+    return B2K_E_NODEVICE;
+  }
+  if (device < 0 || device >= ndev) { set_error("create: device %d of %d", device, ndev); return B2K_E_INVALID; }
+  cudaDeviceProp prop;
+  B2K_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return B2K_E_NODEVICE;
+  }
+  DeviceGuard g(device);
+  b2k_index* ix = new (std::nothrow) b2k_index();
+  if (!ix) { set_error("create: out of host memory"); return B2K_E_NOMEM; }
+  ix->device = device; ix->n_sm = prop.multiProcessorCount; ix->n_tables = n_tables;
+  for (int t = 0; t < n_tables; ++t) ix->dims[t] = table_dims[t];
+  make_col_offsets(ix);
+  ix->cap = capacity_rows; ix->base = base_offset;
+  memset(&ix->stats, 0, sizeof(ix->stats));
+  int rc = 0;
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)) != cudaSuccess) rc = (int)e;
+  if (!rc) rc = dev_alloc(&ix->f32, (size_t)ix->cap * ix->D);
+  if (!rc) rc = dev_alloc(&ix->bf16, (size_t)ix->cap * ix->Dp);
+  if (!rc) rc = dev_alloc(&ix->norm2, (size_t)ix->cap);
+  if (!rc) rc = dev_alloc(&ix->stat_bits, 2);
+  if (!rc && (e = cudaMemset(ix->stat_bits, 0, 2 * sizeof(unsigned int))) != cudaSuccess) rc = (int)e;
+  if (!rc && (e = cudaMallocHost(reinterpret_cast<void**>(&ix->h_fail), 64)) != cudaSuccess) rc = (int)e;
+  for (int i = 0; i < 3 && !rc; ++i)
+    if ((e = cudaEventCreate(&ix->ev[i])) != cudaSuccess) rc = (int)e;
+  if (rc) {
+    if (rc > 0) set_error("create: %s (capacity %lld rows x %d dims)", cudaGetErrorString((cudaError_t)rc),
+                          (long long)capacity_rows, ix->D);
+    cudaGetLastError();
+    b2k_destroy(ix);
+    return rc;
+  }
+  *out = ix;
+  return 0;
+}
+
+void b2k_destroy(b2k_index* ix) {
+  if (!ix) return;
+  DeviceGuard g(ix->device);
+  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  ix->ws.release();
+  dev_free(ix->f32); dev_free(ix->bf16); dev_free(ix->norm2); dev_free(ix->stat_bits);
+  for (int t = 0; t < B2K_MAX_TABLES; ++t) dev_free(ix->stage[t]);
+  dev_free(ix->stage_rows_f32);
+  if (ix->h_fail) cudaFreeHost(ix->h_fail);
+  for (int i = 0; i < 3; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+}
+
+int64_t b2k_capacity(const b2k_index* ix) { return ix ? ix->cap : 0; }
+
+int b2k_reserve(b2k_index* ix, int64_t capacity_rows) {
+  if (!ix || capacity_rows < ix->ntotal || capacity_rows > 0x7fffff00ll) { set_error("reserve: bad capacity"); return B2K_E_INVALID; }
+  if (capacity_rows == ix->cap) return 0;
+  DeviceGuard g(ix->device);
+  B2K_CUDA(cudaDeviceSynchronize());
+  float* nf = nullptr; uint16_t* nb = nullptr; float* nn = nullptr;
+  int rc = dev_alloc(&nf, (size_t)capacity_rows * ix->D);
+  if (!rc) rc = dev_alloc(&nb, (size_t)capacity_rows * ix->Dp);
+  if (!rc) rc = dev_alloc(&nn, (size_t)capacity_rows);
+  cudaError_t e = cudaSuccess;
+  if (!rc && ix->ntotal > 0) {
+    e = cudaMemcpy(nf, ix->f32, (size_t)ix->ntotal * ix->D * 4, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(nb, ix->bf16, (size_t)ix->ntotal * ix->Dp * 2, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(nn, ix->norm2, (size_t)ix->ntotal * 4, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) { set_error("reserve: %s", cudaGetErrorString(e)); rc = (int)e; }
+  }
+  if (rc) { dev_free(nf); dev_free(nb); dev_free(nn); cudaGetLastError(); return rc; }
+  dev_free(ix->f32); dev_free(ix->bf16); dev_free(ix->norm2);
+  ix->f32 = nf; ix->bf16 = nb; ix->norm2 = nn; ix->cap = capacity_rows;
+  ix->tmap_db_ptr = nullptr;
+  return 0;
+}
+
+int b2k_add_device(b2k_index* ix, const float* const* dev_tables, int64_t n, void* stream) {
+  if (!ix || !dev_tables || n < 0) { set_error("add: bad argument"); return B2K_E_INVALID; }
+  if (ix->ntotal + n > ix->cap) {
+    set_error("add: %lld + %lld rows exceed the capacity %lld", (long long)ix->ntotal, (long long)n, (long long)ix->cap);
+    return B2K_E_CAPACITY;
+  }
+  if (n == 0) return 0;
+  DeviceGuard g(ix->device);
+  PackArgs a;
+  fill_pack_args(ix, a, n, ix->ntotal, 1);
+  for (int t = 0; t < ix->n_tables; ++t) a.tables[t] = dev_tables[t];
+  int rc = launch_pack(a, stream ? (cudaStream_t)stream : ix->stream);
+  if (rc) return rc;
+  ix->ntotal += n;
+  return 0;
+}
+
+int b2k_add(b2k_index* ix, const float* const* host_tables, int64_t n) {
+  if (!ix || !host_tables || n < 0) { set_error("add: bad argument"); return B2K_E_INVALID; }
+  if (ix->ntotal + n > ix->cap) {
+    set_error("add: %lld + %lld rows exceed the capacity %lld", (long long)ix->ntotal, (long long)n, (long long)ix->cap);
+    return B2K_E_CAPACITY;
+  }
+  DeviceGuard g(ix->device);
+  int rc = ensure_stage(ix);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < n; r0 += kStageRows) {
+    const int64_t m = std::min(kStageRows, n - r0);
+    const float* devp[B2K_MAX_TABLES];
+    for (int t = 0; t < ix->n_tables; ++t) {
+      B2K_CUDA(cudaMemcpyAsync(ix->stage[t], host_tables[t] + r0 * ix->dims[t], (size_t)m * ix->dims[t] * sizeof(float),
+                               cudaMemcpyHostToDevice, ix->stream));
+      devp[t] = ix->stage[t];
+    }
+    rc = b2k_add_device(ix, devp, m, ix->stream);
+    if (rc) return rc;
+    // the staging buffers are reused by the next chunk and the host arrays are borrowed
+    B2K_CUDA(cudaStreamSynchronize(ix->stream));
+  }
+  return 0;
+}
+
+int64_t b2k_ntotal(const b2k_index* ix) { return ix ? ix->ntotal : 0; }
+int32_t b2k_dim(const b2k_index* ix) { return ix ? ix->D : 0; }
+int32_t b2k_dim_padded(const b2k_index* ix) { return ix ? ix->Dp : 0; }
+int64_t b2k_base_offset(const b2k_index* ix) { return ix ? ix->base : 0; }
+
+int b2k_search_device(b2k_index* ix, const float* q_dev, int32_t nq, int32_t k, float* dist_dev,
+                      int64_t* labels_dev, float* ip_dev, void* stream) {
+  int rc = check_search_args(ix, q_dev, nq, k, dist_dev, labels_dev);
+  if (rc) return rc;
+  DeviceGuard g(ix->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+  rc = ensure_workspace(ix, std::min(nq, kMaxNqPerPass));
+  if (rc) return rc;
+  for (int q0 = 0; q0 < nq; q0 += kMaxNqPerPass) {
+    const int m = std::min(kMaxNqPerPass, nq - q0);
+    rc = search_pass(ix, q_dev + (int64_t)q0 * ix->D, m, k, dist_dev + (int64_t)q0 * k,
+                     labels_dev + (int64_t)q0 * k, ip_dev ? ip_dev + (int64_t)q0 * k : nullptr, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b2k_search(b2k_index* ix, const float* q_host, int32_t nq, int32_t k, float* dist_host,
+               int64_t* labels_host, float* ip_host) {
+  int rc = check_search_args(ix, q_host, nq, k, dist_host, labels_host);
+  if (rc) return rc;
+  DeviceGuard g(ix->device);
+  rc = ensure_workspace(ix, std::min(nq, kMaxNqPerPass));
+  if (rc) return rc;
+  Workspace& w = ix->ws;
+  cudaStream_t st = ix->stream;
+  int n_fail = 0;
+  for (int q0 = 0; q0 < nq; q0 += kMaxNqPerPass) {
+    const int m = std::min(kMaxNqPerPass, nq - q0);
+    B2K_CUDA(cudaMemcpyAsync(w.q, q_host + (int64_t)q0 * ix->D, (size_t)m * ix->D * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    rc = search_pass(ix, w.q, m, k, w.out_dist, w.out_labels, w.out_ip, st);
+    if (rc) return rc;
+    B2K_CUDA(cudaMemcpyAsync(dist_host + (int64_t)q0 * k, w.out_dist, (size_t)m * k * sizeof(float),
+                             cudaMemcpyDeviceToHost, st));
+    B2K_CUDA(cudaMemcpyAsync(labels_host + (int64_t)q0 * k, w.out_labels, (size_t)m * k * sizeof(int64_t),
+                             cudaMemcpyDeviceToHost, st));
+    if (ip_host)
+      B2K_CUDA(cudaMemcpyAsync(ip_host + (int64_t)q0 * k, w.out_ip, (size_t)m * k * sizeof(float),
+                               cudaMemcpyDeviceToHost, st));
+    B2K_CUDA(cudaMemcpyAsync(ix->h_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2K_CUDA(cudaStreamSynchronize(st));
+    n_fail += ix->h_fail[0];
+  }
+  ix->stats.n_uncertified = n_fail;
+  return 0;
+}
+
+int b2k_get_stats(b2k_index* ix, b2k_stats* out) {
+  if (!ix || !out) { set_error("get_stats: bad argument"); return B2K_E_INVALID; }
+  DeviceGuard g(ix->device);
+  B2K_CUDA(cudaDeviceSynchronize());
+  unsigned int bits[2] = {0, 0};
+  B2K_CUDA(cudaMemcpy(bits, ix->stat_bits, sizeof(bits), cudaMemcpyDeviceToHost));
+  float e2, n2;
+  memcpy(&e2, &bits[0], 4); memcpy(&n2, &bits[1], 4);
+  ix->stats.err_max = sqrtf(e2);
+  ix->stats.norm_max = sqrtf(n2);
+  if (ix->ws.fail_count && ix->stats.path != 0 && ix->stats.n_uncertified < 0) {
+    // device API: count of the last pass (the host API sums over passes itself)
+    int32_t nf = 0;
+    B2K_CUDA(cudaMemcpy(&nf, ix->ws.fail_count, sizeof(nf), cudaMemcpyDeviceToHost));
+    ix->stats.n_uncertified = nf;
+  }
+  if (ix->ws.eps_tc && ix->stats.path != 0) {
+    float eps0 = 0.f;
+    B2K_CUDA(cudaMemcpy(&eps0, ix->stats.path == 1 ? ix->ws.eps_scan : ix->ws.eps_tc, sizeof(float),
+                        cudaMemcpyDeviceToHost));
+    ix->stats.eps_max = eps0;   // slack of query 0 of the last pass (representative; per-query on device)
+  }
+  if (ix->ev_valid) {
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, ix->ev[0], ix->ev[1]) == cudaSuccess) ix->stats.score_ms = a;
+    if (cudaEventElapsedTime(&b, ix->ev[1], ix->ev[2]) == cudaSuccess) ix->stats.tail_ms = b;
+    cudaGetLastError();
+  }
+  *out = ix->stats;
+  return 0;
+}
+
+int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
+  if (!ix) { set_error("set_option: null index"); return B2K_E_INVALID; }
+  switch (key) {
+    case B2K_OPT_PATH:
+      if (value < 0 || value > 2) break;
+      ix->opt_path = (int)value; return 0;
+    case B2K_OPT_RERANK:
+      if (value < 32 || value > 8192) break;
+      ix->opt_cand_cap = (int)value; return 0;
+    case B2K_OPT_FORCE_EXACT:
+      ix->opt_force_exact = value != 0; return 0;
+    case B2K_OPT_SCAN_MAX_B:
+      if (value < 0) break;
+      ix->opt_scan_max_b = (int)value; return 0;
+    case B2K_OPT_SPLITS:
+      if (value < 0 || value > 4096) break;
+      ix->opt_splits = (int)value; return 0;
+    default: break;
+  }
+  set_error("set_option: key %d value %lld rejected", key, (long long)value);
+  return B2K_E_INVALID;
+}
+
+int b2k_merge_topk_device(const float* ip, const float* dist, const int64_t* labels, int32_t n_lists,
+                          int32_t nq, int32_t k, float* out_ip, float* out_dist, int64_t* out_labels,
+                          int32_t device, void* stream) {
+  if (!ip || !dist || !labels || !out_dist || !out_labels || n_lists < 1 || nq < 0 || k < 1 || k > B2K_MAX_K ||
+      n_lists * k > 1024) {
+    set_error("merge: bad argument");
+    return B2K_E_INVALID;
+  }
+  DeviceGuard g(device);
+  MergeArgs a;
+  a.ip = ip; a.dist = dist; a.labels = labels; a.n_lists = n_lists; a.nq = nq; a.k = k;
+  a.out_ip = out_ip; a.out_dist = out_dist; a.out_labels = out_labels;
+  return launch_merge(a, (cudaStream_t)stream);
+}
+
+int b2k_normalize_l2(float* x_host, int64_t n, int32_t d, int32_t device) {
+  if (!x_host || n < 0 || d < 1) { set_error("normalize_l2: bad argument"); return B2K_E_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("normalize_l2: no CUDA device (this engine has no CPU path)");
+    return B2K_E_NODEVICE;
+  }
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  float* d_x = nullptr;
+  int rc = dev_alloc(&d_x, (size_t)n * d);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpy(d_x, x_host, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { rc = launch_normalize(d_x, n, d, 0); if (!rc) e = cudaDeviceSynchronize(); }
+  if (e == cudaSuccess && !rc) e = cudaMemcpy(x_host, d_x, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_x);
+  if (e != cudaSuccess) { set_error("normalize_l2: %s", cudaGetErrorString(e)); return (int)e; }
+  return rc;
+}
+
+// ---- persistence -------------------------------------------------------------------------
+int b2k_save(b2k_index* ix, const char* path, const int64_t* ids, int64_t n_ids) {
+  if (!ix || !path) { set_error("save: bad argument"); return B2K_E_INVALID; }
+  if (ids && n_ids != ix->ntotal) { set_error("save: %lld ids for %lld rows", (long long)n_ids, (long long)ix->ntotal); return B2K_E_INVALID; }
+  DeviceGuard g(ix->device);
+  B2K_CUDA(cudaStreamSynchronize(ix->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("save: cannot open %s", path); return B2K_E_IO; }
+  FileHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "B2KIDX01", 8);
+  h.version = 1; h.n_tables = ix->n_tables;
+  for (int t = 0; t < ix->n_tables; ++t) h.dims[t] = ix->dims[t];
+  h.D = ix->D; h.has_ids = ids ? 1 : 0; h.n_rows = ix->ntotal;
+  h.rows_offset = sizeof(FileHeader);
+  h.ids_offset = h.rows_offset + ix->ntotal * (int64_t)ix->D * 4;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  std::vector<float> buf((size_t)std::min<int64_t>(kStageRows, std::max<int64_t>(ix->ntotal, 1)) * ix->D);
+  for (int64_t r0 = 0; ok && r0 < ix->ntotal; r0 += kStageRows) {
+    const int64_t m = std::min(kStageRows, ix->ntotal - r0);
+    cudaError_t e = cudaMemcpy(buf.data(), ix->f32 + r0 * ix->D, (size_t)m * ix->D * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { fclose(f); set_error("save: %s", cudaGetErrorString(e)); return (int)e; }
+    ok = fwrite(buf.data(), (size_t)ix->D * 4, (size_t)m, f) == (size_t)m;
+  }
+  if (ok && ids && ix->ntotal > 0) ok = fwrite(ids, 8, (size_t)ix->ntotal, f) == (size_t)ix->ntotal;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { set_error("save: write to %s failed", path); return B2K_E_IO; }
+  return 0;
+}
+
+int b2k_file_info(const char* path, int64_t* n_rows, int32_t* n_tables, int32_t* table_dims, int32_t* has_ids) {
+  if (!path) { set_error("file_info: null path"); return B2K_E_INVALID; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("file_info: cannot open %s", path); return B2K_E_IO; }
+  FileHeader h;
+  int rc = read_header(f, h, path);
+  fclose(f);
+  if (rc) return rc;
+  if (n_rows) *n_rows = h.n_rows;
+  if (n_tables) *n_tables = h.n_tables;
+  if (table_dims) for (int t = 0; t < h.n_tables; ++t) table_dims[t] = h.dims[t];
+  if (has_ids) *has_ids = h.has_ids;
+  return 0;
+}
+
+int b2k_load_ids(const char* path, int64_t row_begin, int64_t n, int64_t* ids_out) {
+  if (!path || !ids_out || row_begin < 0 || n < 0) { set_error("load_ids: bad argument"); return B2K_E_INVALID; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("load_ids: cannot open %s", path); return B2K_E_IO; }
+  FileHeader h;
+  int rc = read_header(f, h, path);
+  if (!rc && (!h.has_ids || row_begin + n > h.n_rows)) { set_error("load_ids: %s holds no ids for that range", path); rc = B2K_E_IO; }
+  if (!rc && (fseek(f, (long)(h.ids_offset + row_begin * 8), SEEK_SET) != 0 ||
+              fread(ids_out, 8, (size_t)n, f) != (size_t)n)) { set_error("load_ids: short read"); rc = B2K_E_IO; }
+  fclose(f);
+  return rc;
+}
+
+int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_end, b2k_index** out) {
+  if (!path || !out) { set_error("load: bad argument"); return B2K_E_INVALID; }
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("load: cannot open %s", path); return B2K_E_IO; }
+  FileHeader h;
+  int rc = read_header(f, h, path);
+  if (rc) { fclose(f); return rc; }
+  if (row_end < 0 || row_end > h.n_rows) row_end = h.n_rows;
+  if (row_begin < 0 || row_begin > row_end) { fclose(f); set_error("load: bad row range"); return B2K_E_INVALID; }
+  const int64_t n = row_end - row_begin;
+  b2k_index* ix = nullptr;
+  rc = b2k_create(h.dims, h.n_tables, n, device, row_begin, &ix);
+  if (rc) { fclose(f); return rc; }
+  if (ix->D != h.D) { fclose(f); b2k_destroy(ix); set_error("load: corrupt header"); return B2K_E_IO; }
+  DeviceGuard g(device);
+  rc = dev_alloc(&ix->stage_rows_f32, (size_t)kStageRows * ix->D);
+  std::vector<float> buf((size_t)std::min<int64_t>(kStageRows, std::max<int64_t>(n, 1)) * ix->D);
+  if (!rc && fseek(f, (long)(h.rows_offset + row_begin * (int64_t)ix->D * 4), SEEK_SET) != 0) { set_error("load: seek failed"); rc = B2K_E_IO; }
+  for (int64_t r0 = 0; !rc && r0 < n; r0 += kStageRows) {
+    const int64_t m = std::min(kStageRows, n - r0);
+    if (fread(buf.data(), (size_t)ix->D * 4, (size_t)m, f) != (size_t)m) { set_error("load: short read in %s", path); rc = B2K_E_IO; break; }
+    cudaError_t e = cudaMemcpyAsync(ix->stage_rows_f32, buf.data(), (size_t)m * ix->D * 4, cudaMemcpyHostToDevice, ix->stream);
+    if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; break; }
+    // stored rows are already normalised: re-pack without scaling (same per-table sums -> same norm2 bits)
+    PackArgs a;
+    fill_pack_args(ix, a, m, r0, 0);
+    for (int t = 0; t < ix->n_tables; ++t) { a.tables[t] = ix->stage_rows_f32 + ix->col_off[t]; a.strides[t] = ix->D; }
+    rc = launch_pack(a, ix->stream);
+    if (!rc) { e = cudaStreamSynchronize(ix->stream); if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; } }
+  }
+  fclose(f);
+  if (rc) { b2k_destroy(ix); return rc; }
+  ix->ntotal = n;
+  *out = ix;
+  return 0;
+}
+
+int b2k_get_rows(b2k_index* ix, int64_t row0, int64_t n, float* f32_host, uint16_t* bf16_host, float* norm2_host) {
+  if (!ix || row0 < 0 || n < 0 || row0 + n > ix->ntotal) { set_error("get_rows: bad range"); return B2K_E_INVALID; }
+  DeviceGuard g(ix->device);
+  B2K_CUDA(cudaStreamSynchronize(ix->stream));
+  if (f32_host) B2K_CUDA(cudaMemcpy(f32_host, ix->f32 + row0 * ix->D, (size_t)n * ix->D * 4, cudaMemcpyDeviceToHost));
+  if (bf16_host) B2K_CUDA(cudaMemcpy(bf16_host, ix->bf16 + row0 * ix->Dp, (size_t)n * ix->Dp * 2, cudaMemcpyDeviceToHost));
+  if (norm2_host) B2K_CUDA(cudaMemcpy(norm2_host, ix->norm2 + row0, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- synthetic data ------------------------------------------------------------------------
+static void fill_synth_args(const b2k_index* ix, SynthArgs& s, const b2k_synth* p) {
+  memset(&s, 0, sizeof(s));
+  s.n_tables = ix->n_tables;
+  for (int t = 0; t < ix->n_tables; ++t) { s.dims[t] = ix->dims[t]; s.tables[t] = ix->stage[t]; }
+  s.seed = p->seed; s.n_clusters = p->n_clusters > 0 ? p->n_clusters : 4096;
+  s.sigma = p->sigma; s.abs_mask = p->abs_mask; s.total_rows = p->total_rows;
+}
+
+int b2k_fill_synthetic(b2k_index* ix, int64_t n, const b2k_synth* p) {
+  if (!ix || !p || n < 0) { set_error("fill_synthetic: bad argument"); return B2K_E_INVALID; }
+  if (ix->ntotal + n > ix->cap) { set_error("fill_synthetic: beyond capacity"); return B2K_E_CAPACITY; }
+  DeviceGuard g(ix->device);
+  int rc = ensure_stage(ix);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < n; r0 += kStageRows) {
+    const int64_t m = std::min(kStageRows, n - r0);
+    SynthArgs s;
+    fill_synth_args(ix, s, p);
+    s.query_mode = 0; s.n = m; s.first = ix->base + ix->ntotal;
+    rc = launch_synth(s, ix->stream);
+    if (rc) return rc;
+    const float* devp[B2K_MAX_TABLES];
+    for (int t = 0; t < ix->n_tables; ++t) devp[t] = ix->stage[t];
+    rc = b2k_add_device(ix, devp, m, ix->stream);   // same stream: ordered after the generator
+    if (rc) return rc;
+  }
+  B2K_CUDA(cudaStreamSynchronize(ix->stream));
+  return 0;
+}
+
+int b2k_synth_queries_device(b2k_index* ix, int32_t nq, const b2k_synth* p, uint64_t qseed, float sigma_q,
+                             float* q_dev, void* stream) {
+  if (!ix || !p || !q_dev || nq < 0 || nq > kStageRows || p->total_rows < 1) {
+    set_error("synth_queries: bad argument (nq <= %lld)", (long long)kStageRows);
+    return B2K_E_INVALID;
+  }
+  DeviceGuard g(ix->device);
+  int rc = ensure_stage(ix);
+  if (rc) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+  SynthArgs s;
+  fill_synth_args(ix, s, p);
+  s.query_mode = 1; s.n = nq; s.first = 0; s.qseed = qseed; s.sigma_q = sigma_q;
+  rc = launch_synth(s, st);
+  if (rc) return rc;
+  // parts -> unit norm (extractor output), concatenated; then whole-vector normalise
+  PackArgs a;
+  fill_pack_args(ix, a, nq, 0, 1);
+  for (int t = 0; t < ix->n_tables; ++t) a.tables[t] = ix->stage[t];
+  a.out_f32 = q_dev; a.out_bf16 = nullptr; a.out_norm2 = nullptr; a.stat_bits = nullptr;
+  rc = launch_pack(a, st);
+  if (rc) return rc;
+  return launch_normalize(q_dev, nq, ix->D, st);
+}
+
+}  // extern "C"

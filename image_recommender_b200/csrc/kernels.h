@@ -9,6 +9,7 @@ namespace b2k {
 struct PackArgs {
   const float* tables[B2K_MAX_TABLES];  // device [n, d_t]
   int32_t dims[B2K_MAX_TABLES];
+  int32_t strides[B2K_MAX_TABLES];  // input row stride of table t in floats (d_t when dense)
   int32_t col_off[B2K_MAX_TABLES];
   int32_t n_tables;
   int32_t D, Dp;
@@ -28,7 +29,6 @@ struct QueryPrepArgs {
   float* eps_scan;      // [nq]
   float* eps_tc;        // [nq]
   const unsigned int* stat_bits;
-  float acc_rel;
   int32_t nq, nq_pad, D, Dp;
 };
 
@@ -52,41 +52,47 @@ struct ScanArgs {
   int32_t nq;           // total queries
   int32_t q0;           // first query of this pass
   int32_t n_splits;     // == gridDim.x
-  Cand* partial;        // [nq, n_splits, kList]
+  Cand* partial;        // [nq, n_lists, kList]; this kernel fills list `split`
+  int32_t n_lists;
 };
 
 struct SelectArgs {
-  const Cand* partial;  // [nq, n_splits, kList]
-  int32_t n_splits;
-  int32_t n_rerank;     // C'
-  int32_t* cand_rows;   // [nq, C']
-  float* thr;           // [nq]
+  const Cand* partial;  // [nq, list_stride, kList] approximate (bf16) scores
+  int32_t n_lists;      // lists [0, n_lists) of each query are in use
+  int32_t list_stride;
+  int32_t k;
+  const float* eps;     // [nq] bound on |approximate - exact| for the path that filled `partial`
+  int32_t cand_cap;     // candidate slots per query
+  int32_t force_exact;
+  int32_t* cand_rows;   // [nq, cand_cap]
+  int32_t* cand_count;  // [nq]
+  int32_t* flags;       // [nq] 0 = certified; bit0 saturated list, bit1 overflow, bit2 forced
+  float* thr;           // [nq] candidate threshold b_k - 2 eps
 };
 
 struct RerankArgs {
   const float* db_f32;  // [n_rows, D]
   const float* q;       // [nq, D]
-  const int32_t* cand_rows;  // [nq, C']
-  float* cand_ip;       // [nq, C']
-  int32_t nq, n_rerank, D;
+  const int32_t* cand_rows;   // [nq, cand_cap]
+  const int32_t* cand_count;  // [nq]
+  float* cand_ip;       // [nq, cand_cap] exact scores (Spec R)
+  int32_t nq, cand_cap, D;
 };
 
 struct FinalizeArgs {
   const int32_t* cand_rows;
+  const int32_t* cand_count;
   const float* cand_ip;
-  const float* thr;
-  const float* eps;       // per query slack of the path that produced the candidates
+  const int32_t* flags;
   const float* qn2;
   const float* norm2;     // per DB row
-  int32_t nq, n_rerank, k;
+  int32_t nq, cand_cap, k;
   int64_t base_offset;
-  int32_t force_exact;
   float* out_ip;          // [nq, k] (may be null)
   float* out_dist;        // [nq, k]
   int64_t* out_labels;    // [nq, k]
   int32_t* fail_count;    // [1]
   int32_t* fail_list;     // [nq]
-  float* eps_max_bits;    // [1] (as uint bits)
 };
 
 struct ExactArgs {
@@ -122,7 +128,7 @@ bool scan_supports(int Dp);
 int launch_scan(const ScanArgs& a, int n_queries_this_pass, cudaStream_t st);
 
 int launch_select(const SelectArgs& a, int nq, cudaStream_t st);
-int launch_rerank(const RerankArgs& a, cudaStream_t st);
+int launch_rerank(const RerankArgs& a, int n_sm, cudaStream_t st);
 int launch_finalize(const FinalizeArgs& a, cudaStream_t st);
 int exact_num_splits(int n_sm);
 int launch_exact(const ExactArgs& a, cudaStream_t st);   // scan + finalize of failed queries
@@ -141,7 +147,8 @@ struct ScoreTcArgs {
   int32_t Dp;
   int32_t nq;
   ScoreTcPlan plan;
-  Cand* partial;        // [nq, n_splits, kList]
+  Cand* partial;        // [nq, n_lists, kList]; CTA (qtile, split) fills list `split`
+  int32_t n_lists;
 };
 bool score_tc_supports(int Dp);
 ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits);

@@ -25,7 +25,7 @@ pack_rows_kernel(PackArgs a) {
   for (int t = 0; t < a.n_tables; ++t) {
     const int d = a.dims[t];
     const int off = a.col_off[t];
-    const float* __restrict__ x = a.tables[t] + warp * (int64_t)d;
+    const float* __restrict__ x = a.tables[t] + warp * (int64_t)a.strides[t];
     float inv = 1.0f;
     if (a.normalize) {
       const float s = warp_sum_f32(lane_sumsq(x, d, lane));
@@ -99,10 +99,14 @@ normalize_rows_kernel(float* __restrict__ x, int64_t n, int d) {
   for (int i = lane; i < d; i += 32) row[i] = __fmul_rn(row[i], inv);
 }
 
-// Query prep: fp32 [nq, D] -> bf16 [nq_pad, Dp] (zero padded), ||q||², and the per-query
-// certificate slack  eps = (||bf16(q)||·err_max + ||q - bf16(q)||·norm_max)·(1+2^-10)
-//                          + acc_rel · D · ||bf16(q)|| · norm_max
-// (err_max / norm_max come from the shard's pack statistics; see DESIGN.md "certificate").
+// Query prep: fp32 [nq, D] -> bf16 [nq_pad, Dp] (zero padded), ||q||², and the per-query bound
+// eps >= |approximate score - exact score| over every row of the shard (DESIGN.md "certificate"):
+//   tensor path : q_b·x_b vs q·x  ->  ||q_b||·E + ||q - q_b||·(X + E) + D·2^-22·||q_b||·(X + E)
+//   scan path   : q·x_b   vs q·x  ->  ||q||·E                      + D·2^-23·||q||·(X + E)
+// with E = max_r ||bf16(x_r) - x_r||, X = max_r ||x_r|| from the shard's pack statistics; the
+// last terms bound the fp32 accumulation (tensor core: 4 ulp per accumulated product assumed).
+// Every norm is inflated by 1.001 against its own rounding; + 2^-23·||q||·X covers Spec R's
+// single rounding.
 __global__ void __launch_bounds__(256)
 query_prep_kernel(QueryPrepArgs a) {
   const int lane = threadIdx.x & 31;
@@ -131,13 +135,13 @@ query_prep_kernel(QueryPrepArgs a) {
   const float qb2 = warp_sum_f32(pb), qd2 = warp_sum_f32(pd);
   if (lane == 0) {
     a.qn2[w] = qn2;
-    const float err_max = sqrtf(__uint_as_float(a.stat_bits[0])) * 1.001f;
-    const float norm_max = sqrtf(__uint_as_float(a.stat_bits[1])) * 1.001f;
+    const float E = sqrtf(__uint_as_float(a.stat_bits[0])) * 1.001f;
+    const float X = sqrtf(__uint_as_float(a.stat_bits[1])) * 1.001f;
     const float qb = sqrtf(qb2) * 1.001f, qd = sqrtf(qd2) * 1.001f, qn = sqrtf(qn2) * 1.001f;
-    // K-scan path multiplies the fp32 query with bf16 rows in fp32 FMAs: no query rounding.
-    const float acc = a.acc_rel * (float)a.D * norm_max;
-    a.eps_scan[w] = qn * err_max * 1.001f + acc * qn;
-    a.eps_tc[w] = (qb * err_max + qd * norm_max) * 1.001f + acc * qb;
+    const float XE = X + E;
+    const float r1 = 1.1920929e-07f * qn * X;                       // 2^-23
+    a.eps_scan[w] = qn * E * 1.001f + (float)a.D * 1.1920929e-07f * qn * XE + r1;
+    a.eps_tc[w] = (qb * E + qd * XE) * 1.001f + (float)a.D * 2.3841858e-07f * qb * XE + r1;
   }
 }
 

@@ -35,8 +35,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spin with a watchdog: a protocol bug must surface as a launch failure (trap), never as a
+// hung GPU.  try_wait itself suspends for a HW-defined time slice, so 2^26 rounds >> seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
   }
 }
 

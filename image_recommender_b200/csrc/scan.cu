@@ -33,20 +33,16 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
   return v;
 }
 
-// Insert (s,row) into the lane-per-entry list `lst` (shared, 32 Cands) if it beats the
-// current minimum; returns the new threshold (min score when the list is full, else -inf).
+// Insert (s,row) into the lane-per-entry list `lst` (shared, 32 Cands), replacing the worst
+// entry (lowest key; empty slots first).  Returns the new threshold: the worst score when the
+// list is full, else -inf.  Callers only insert entries that beat the current threshold.
 __device__ __forceinline__ float warp_list_insert(Cand* lst, int lane, float s, int32_t row) {
   Cand e = lst[lane];
-  // (key, lane) so that exactly one lane owns the minimum even among empty slots
-  uint64_t k = cand_key(e.score, e.row);
-  uint64_t kl = (k & ~31ull) | (uint64_t)lane;  // low 5 bits of the row field are irrelevant for min-pick
-  // Using the masked key only to pick a victim; exact comparison below uses full keys.
-  uint64_t kmin = warp_min_u64(kl);
-  // among candidates whose masked key equals the min prefix choose by full key then lane
-  bool is_victim = (kl == kmin);
-  if (is_victim) { e.score = s; e.row = row; lst[lane] = e; }
+  const uint64_t k = cand_key(e.score, e.row);
+  const uint64_t kmin = warp_min_u64(k);
+  const unsigned vm = __ballot_sync(0xffffffffu, k == kmin);   // ties only among empty slots
+  if (lane == __ffs(vm) - 1) { e.score = s; e.row = row; lst[lane] = e; }
   __syncwarp();
-  // new threshold
   float sc = e.row < 0 ? -INFINITY : e.score;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sc = fminf(sc, __shfl_xor_sync(0xffffffffu, sc, o));
@@ -209,7 +205,7 @@ scan_bf16_kernel(ScanArgs a, int n_stages, int stage_bytes) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int qi = a.q0 + q;
-      if (qi < a.nq) a.partial[((int64_t)qi * a.n_splits + split) * kList + lane] = lists[q * 32 + lane];
+      if (qi < a.nq) a.partial[((int64_t)qi * a.n_lists + split) * kList + lane] = lists[q * 32 + lane];
     }
   }
 }
@@ -318,17 +314,12 @@ exact_scan_kernel(ExactArgs a) {
 #pragma unroll
       for (int f = 0; f < kExactFQ; ++f) {
         const float ip = (float)warp_sum_f64(p[f]);
-        if (ip > tau[f] || (ip == tau[f] && false)) {
+        if (ip > tau[f]) {   // equal scores: the earlier (lower) row already listed wins
           // replace the warp list's minimum (lane-per-entry, in registers)
           const uint64_t k = cand_key(e_s[f], e_r[f]);
-          const uint64_t kl = (k & ~31ull) | (uint64_t)lane;
-          uint64_t kmin = kl;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const uint64_t u = __shfl_xor_sync(0xffffffffu, kmin, o);
-            kmin = u < kmin ? u : kmin;
-          }
-          if (kl == kmin) { e_s[f] = ip; e_r[f] = (int32_t)row; }
+          const uint64_t kmin = warp_min_u64(k);
+          const unsigned vm = __ballot_sync(0xffffffffu, k == kmin);
+          if (lane == __ffs(vm) - 1) { e_s[f] = ip; e_r[f] = (int32_t)row; }
           float sc = e_r[f] < 0 ? -INFINITY : e_s[f];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sc = fminf(sc, __shfl_xor_sync(0xffffffffu, sc, o));

@@ -1,0 +1,289 @@
+// K-score: batched approximate scoring S = Q · Xᵀ on the 5th-gen tensor cores with the
+// running top-32 selection fused into the epilogue, so the [nq, n_rows] score matrix never
+// reaches HBM.  Replaces the contraction inside index.search(query_vec, top_k)
+// (main/search_from_image.py:247) for query batches (a new-build extension: the reference
+// is batch-1).
+//
+// Work decomposition: CTA = (query tile of 128, DB split).  blockIdx = split * n_qtiles + qtile
+// so that CTAs resident at the same time share DB rows through L2.  Per CTA:
+//   warp 0   TMA producer: per K-block of 64 one box of the query tile [128 x 64] and one box of
+//            the DB tile [256 x 64] (bf16, 128-byte swizzle) into a 4-stage shared-memory ring
+//   warp 1   allocates TMEM (512 columns = two 128x256 fp32 accumulators) and issues
+//            tcgen05.mma.cta_group::1.kind::f16  M=128 N=256 K=16, 4 per K-block
+//   warps 2-5 epilogue: tcgen05.ld 32x32b (thread = query row, 32 DB columns per load),
+//            per-thread threshold filter, per-thread top-32 list in shared memory
+// Pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), all mbarrier.
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b2k {
+
+namespace {
+
+constexpr int kBlockM = 128;           // queries per CTA (TMEM lanes)
+constexpr int kBlockN = 256;           // DB rows per accumulator (TMEM columns)
+constexpr int kBlockK = 64;            // bf16 elements per K-block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kListBytes = kList * kBlockM * 8;  // scores + rows
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kListBytes + 256;
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);      // start address  [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
+                            ((uint32_t)(kBlockM >> 4) << 24);
+
+// Replace the worst entry (slot min_e) of a per-thread list and rescan for the new worst.
+// Returns (new worst slot << 32) | bits(new worst score); the score is the admission threshold.
+__device__ __noinline__ uint64_t list_insert(float* my_s, int32_t* my_r, int min_e, float sc, int32_t row) {
+  my_s[min_e * kBlockM] = sc;
+  my_r[min_e * kBlockM] = row;
+  float mn = INFINITY;
+  int me = 0;
+#pragma unroll
+  for (int e = 0; e < kList; ++e) {
+    const float se = my_s[e * kBlockM];
+    if (se < mn) { mn = se; me = e; }
+  }
+  return ((uint64_t)(uint32_t)me << 32) | (uint64_t)__float_as_uint(mn);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
+                int32_t n_lists, Cand* __restrict__ partial) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* ring = smem;
+  float* lscore = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);   // [32][128]
+  int32_t* lrow = reinterpret_cast<int32_t*>(lscore + kList * kBlockM);             // [32][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(lrow + kList * kBlockM);
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;      // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;           // [2] accumulator drained
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x % n_qtiles;
+  const int split = blockIdx.x / n_qtiles;
+  const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
+  const int64_t tile_begin = tiles_total * split / n_splits;
+  const int64_t tile_end = tiles_total * (split + 1) / n_splits;
+  const int n_tiles = (int)(tile_end - tile_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { ptx::tma_prefetch_desc(&tmap_q); ptx::tma_prefetch_desc(&tmap_db); }
+  if (warp == 1) { ptx::tmem_alloc(tmem_base_slot, kTmemCols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int32_t row0 = (int32_t)((tile_begin + t) * kBlockN);
+        for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+          const int s = it % kStages;
+          ptx::mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+          unsigned char* a_dst = ring + (size_t)s * kStageBytes;
+          unsigned char* b_dst = a_dst + kABytes;
+          ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+          ptx::tma_load_2d(a_dst, &tmap_q, kb * kBlockK, qtile * kBlockM, &full[s], ptx::kEvictLast);
+          ptx::tma_load_2d(b_dst, &tmap_db, kb * kBlockK, row0, &full[s], ptx::kEvictNormal);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    int it = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = t & 1;
+      ptx::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBlockN);
+      for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+        const int s = it % kStages;
+        ptx::mbar_wait(&full[s], (it / kStages) & 1);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * kStageBytes);
+          const uint64_t a_desc = make_sw128_desc(a_addr);
+          const uint64_t b_desc = make_sw128_desc(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 bytes (16 bf16) inside the swizzled row: +2 in 16-byte units
+            ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc,
+                           (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
+          if (kb == n_kblocks - 1) ptx::umma_commit(&tfull[acc]);   // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+    const int m = quarter * 32 + lane;               // query row inside the tile
+    const int qi = qtile * kBlockM + m;
+    float* my_s = lscore + m;                        // entry e at my_s[e * 128]
+    int32_t* my_r = lrow + m;
+#pragma unroll
+    for (int e = 0; e < kList; ++e) { my_s[e * kBlockM] = -INFINITY; my_r[e * kBlockM] = -1; }
+    float thr = -INFINITY;
+    int min_e = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = t & 1;
+      const int64_t row0 = (tile_begin + t) * kBlockN;
+      const int valid = (int)min((int64_t)kBlockN, n_rows - row0);
+      ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        ptx::tmem_ld_wait();
+        float mx = -INFINITY;
+        const int nvalid = valid - c * 32;           // columns of this chunk that are real rows
+        if (nvalid >= 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= nvalid) v[j] = 0xff800000u;     // -inf: never inserted
+            mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        }
+        if (mx > thr) {
+          // rare after warm-up; statically indexed so v[] stays in registers
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sc = __uint_as_float(v[j]);
+            if (sc > thr) {
+              const uint64_t r = list_insert(my_s, my_r, min_e, sc, (int32_t)(row0 + c * 32 + j));
+              thr = __uint_as_float((uint32_t)r);
+              min_e = (int)(r >> 32);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+    }
+    if (qi < nq) {
+      Cand* out = partial + ((int64_t)qi * n_lists + split) * kList;
+#pragma unroll 4
+      for (int e = 0; e < kList; ++e) {
+        Cand c; c.score = my_s[e * kBlockM]; c.row = my_r[e * kBlockM];
+        out[e] = c;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ---------------------------------------------------------------------------------------
+bool score_tc_supports(int Dp) { return Dp >= kBlockK && (Dp % kBlockK) == 0; }
+
+ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) {
+  ScoreTcPlan p;
+  p.n_qtiles = (nq + kBlockM - 1) / kBlockM;
+  const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
+  int splits = forced_splits > 0 ? forced_splits : n_sm;
+  if ((int64_t)splits > tiles_total) splits = (int)(tiles_total > 0 ? tiles_total : 1);
+  p.n_splits = splits;
+  p.grid = p.n_qtiles * p.n_splits;
+  return p;
+}
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return B2K_E_NODEVICE; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return B2K_E_INVALID; }
+  return 0;
+}
+}  // namespace
+
+int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_bf16, int nq_pad,
+                         const uint16_t* db_bf16, int64_t n_rows, int Dp) {
+  if (tmap_q_out) {
+    int rc = encode_2d(reinterpret_cast<CUtensorMap*>(tmap_q_out), q_bf16, (uint64_t)nq_pad, (uint64_t)Dp, kBlockM);
+    if (rc) return rc;
+  }
+  if (tmap_db_out) {
+    int rc = encode_2d(reinterpret_cast<CUtensorMap*>(tmap_db_out), db_bf16, (uint64_t)n_rows, (uint64_t)Dp, kBlockN);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st) {
+  B2K_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  const CUtensorMap* mq = reinterpret_cast<const CUtensorMap*>(a.tmap_q);
+  const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(a.tmap_db);
+  score_tc_kernel<<<a.plan.grid, kThreads, kSmemBytes, st>>>(*mq, *md, a.n_rows, a.Dp / kBlockK, a.nq,
+                                                            a.plan.n_qtiles, a.plan.n_splits, a.n_lists,
+                                                            a.partial);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace b2k

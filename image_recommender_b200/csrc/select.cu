@@ -1,0 +1,307 @@
+// K-select / K-rerank / K-finalize / K-merge: everything between the approximate (bf16)
+// partial lists and the exact fp32 result of index.search (main/search_from_image.py:247).
+//
+//   select   : per query, b_k = k-th best bf16 score over all partial lists; every listed row
+//              with bf16 score >= b_k - 2*eps becomes a re-rank candidate.  Since
+//              |bf16 score - exact score| <= eps for every row of the shard, the exact top-k is
+//              a subset of those rows PROVIDED no partial list is saturated (all 32 entries
+//              above the threshold): that is the certificate.  Uncertified queries are served
+//              by the exhaustive fp32 scan (scan.cu: K-exact).
+//   rerank   : exact score (Spec R: fp64 accumulation of fp32 products, one rounding) of every
+//              candidate, one warp per (query, candidate); gathers rows from the fp32 copy.
+//   finalize : per query top-k of the candidates by (score desc, row asc); converts to the
+//              squared-L2 distance the reference's METRIC_L2 index returns
+//              (main/create_index.py:219,230) and to global offsets.
+//   merge    : cross-shard merge of per-GPU top-k lists.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2k {
+
+namespace {
+
+constexpr int kSelThreads = 256;
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = u > v ? u : v;
+  }
+  return v;
+}
+
+// Block-wide max of a u64 (all threads get the result).  `scratch` has >= 33 slots.
+__device__ __forceinline__ uint64_t block_max_u64(uint64_t v, uint64_t* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max_u64(v);
+  __syncthreads();                       // scratch reuse across calls
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < (blockDim.x >> 5) ? scratch[lane] : 0ull;
+    w = warp_max_u64(w);
+    if (lane == 0) scratch[32] = w;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// One CTA per query.  Dynamic smem: n_lists*32 u32 score keys.
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(SelectArgs a) {
+  extern __shared__ uint32_t skey[];
+  __shared__ uint64_t scratch[33];
+  __shared__ int s_count, s_sat;
+  const int q = blockIdx.x;
+  const int E = a.n_lists * kList;
+  const Cand* lst = a.partial + (int64_t)q * a.list_stride * kList;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_count = 0; s_sat = 0; }
+
+  for (int e = tid; e < E; e += kSelThreads) {
+    const Cand c = lst[e];
+    skey[e] = c.row < 0 ? 0u : float_key(c.score);   // real scores have key >= 1 (NaN -> 0: dropped)
+  }
+  __syncthreads();
+
+  // b_k: walk distinct score keys downward until k entries are covered.
+  // packs (key << 32 | multiplicity-capped count) so one block reduction does both.
+  uint32_t prev = 0xffffffffu;   // exclusive upper bound (no finite float has this key)
+  int covered = 0;
+  uint32_t bk = 0u;
+  for (int it = 0; it < a.k; ++it) {
+    uint32_t m = 0u;
+    for (int e = tid; e < E; e += kSelThreads) {
+      const uint32_t v = skey[e];
+      if (v < prev && v > m) m = v;
+    }
+    const uint32_t gmax = (uint32_t)block_max_u64((uint64_t)m, scratch);
+    if (gmax == 0u) { bk = 0u; break; }            // fewer than k real entries
+    int c = 0;
+    for (int e = tid; e < E; e += kSelThreads) c += (skey[e] == gmax);
+    // count via block reduction on the same scratch (sum fits: E < 2^31)
+    uint64_t tot = (uint64_t)c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = tot;
+    __syncthreads();
+    uint64_t all = 0;
+    for (int w = 0; w < (kSelThreads >> 5); ++w) all += scratch[w];
+    covered += (int)all;
+    bk = gmax; prev = gmax;
+    if (covered >= a.k) break;
+  }
+  // threshold (in score space).  bk == 0: fewer than k rows listed -> everything is a candidate.
+  float thr = -INFINITY;
+  if (bk != 0u && covered >= a.k) {
+    const uint32_t b = (bk & 0x80000000u) ? (bk & 0x7fffffffu) : ~bk;
+    const float bks = __uint_as_float(b);
+    thr = __fsub_rd(bks, __fmul_ru(2.0f, a.eps[q]));   // round the threshold down: conservative
+  }
+
+  // candidates + saturation.  Warp w owns lists w, w+8, ...; lane j = entry j of the list.
+  int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
+  for (int l = warp; l < a.n_lists; l += (kSelThreads >> 5)) {
+    const Cand c = lst[l * kList + lane];
+    const bool real = c.row >= 0 && skey[l * kList + lane] != 0u;
+    const bool hit = real && (c.score >= thr);
+    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+    const unsigned rm = __ballot_sync(0xffffffffu, c.row >= 0);
+    if (hm == 0xffffffffu && rm == 0xffffffffu && lane == 0) s_sat = 1;   // list full and all at risk
+    if (hm) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_count, __popc(hm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hit) {
+        const int pos = base + __popc(hm & ((1u << lane) - 1u));
+        if (pos < a.cand_cap) out_rows[pos] = c.row;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int cnt = s_count;
+    int flag = 0;
+    if (s_sat) flag |= 1;                       // a list may hide at-risk rows
+    if (cnt > a.cand_cap) { flag |= 2; cnt = a.cand_cap; }
+    if (a.force_exact) flag |= 4;
+    a.cand_count[q] = cnt;
+    a.flags[q] = flag;
+    a.thr[q] = thr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// grid = (blocks_per_query, nq); warp-per-candidate, Spec R.
+__global__ void __launch_bounds__(256)
+rerank_kernel(RerankArgs a) {
+  const int q = blockIdx.y;
+  const int cnt = a.cand_count[q];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int w0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int wstride = gridDim.x * wpb;
+  const float* __restrict__ qv = a.q + (int64_t)q * a.D;
+  const bool vec = ((a.D & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(a.db_f32) & 15) == 0);
+  for (int c = w0; c < cnt; c += wstride) {
+    const int32_t row = a.cand_rows[(int64_t)q * a.cand_cap + c];
+    const float* __restrict__ x = a.db_f32 + (int64_t)row * a.D;
+    double p = 0.0;
+    if (vec) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      const float4* q4 = reinterpret_cast<const float4*>(qv);
+      for (int i = lane; i < (a.D >> 2); i += 32) {
+        const float4 v = __ldg(x4 + i);
+        const float4 w = __ldg(q4 + i);
+        p = __fma_rn((double)w.x, (double)v.x, p);
+        p = __fma_rn((double)w.y, (double)v.y, p);
+        p = __fma_rn((double)w.z, (double)v.z, p);
+        p = __fma_rn((double)w.w, (double)v.w, p);
+      }
+    } else {
+      for (int i4 = lane; i4 * 4 < a.D; i4 += 32)
+        for (int j = 0; j < 4; ++j) {
+          const int i = i4 * 4 + j;
+          if (i < a.D) p = __fma_rn((double)qv[i], (double)x[i], p);
+        }
+    }
+    const float ip = (float)warp_sum_f64(p);
+    if (lane == 0) a.cand_ip[(int64_t)q * a.cand_cap + c] = ip;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// One CTA per query: top-k of the re-ranked candidates.  Dynamic smem: cand_cap u64 keys.
+__global__ void __launch_bounds__(kSelThreads)
+finalize_kernel(FinalizeArgs a) {
+  extern __shared__ uint64_t fkeys[];
+  __shared__ uint64_t scratch[33];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int flag = a.flags[q];
+  if (flag != 0) {
+    if (tid == 0) {
+      const int slot = atomicAdd(a.fail_count, 1);
+      a.fail_list[slot] = q;
+    }
+    return;   // K-exact writes this query's outputs
+  }
+  const int cnt = a.cand_count[q];
+  for (int c = tid; c < cnt; c += kSelThreads)
+    fkeys[c] = cand_key(a.cand_ip[(int64_t)q * a.cand_cap + c], a.cand_rows[(int64_t)q * a.cand_cap + c]);
+  __syncthreads();
+  uint64_t prev = ~0ull;
+  const float qn2 = a.qn2[q];
+  for (int j = 0; j < a.k; ++j) {
+    uint64_t m = 0ull;
+    for (int c = tid; c < cnt; c += kSelThreads) {
+      const uint64_t v = fkeys[c];
+      if (v < prev && v > m) m = v;
+    }
+    const uint64_t best = block_max_u64(m, scratch);
+    prev = best == 0ull ? 0ull : best;
+    if (tid == 0) {
+      float ip = -3.402823466e38f, dist = 3.402823466e38f;
+      int64_t lab = -1;
+      if (best != 0ull) {
+        const int32_t row = key_row(best);
+        ip = key_score(best);
+        lab = a.base_offset + row;
+        dist = fmaxf(__fmaf_rn(-2.0f, ip, __fadd_rn(qn2, a.norm2[row])), 0.f);
+      }
+      if (a.out_ip) a.out_ip[(int64_t)q * a.k + j] = ip;
+      a.out_dist[(int64_t)q * a.k + j] = dist;
+      a.out_labels[(int64_t)q * a.k + j] = lab;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// One warp per query; n_lists*k <= 32*32 entries.  Order: higher ip, then lower offset.
+__global__ void __launch_bounds__(128)
+merge_kernel(MergeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= a.nq) return;
+  const int E = a.n_lists * a.k;
+  uint32_t last_key = 0xffffffffu;
+  int64_t last_off = -1;            // entries strictly after (last_key, last_off) remain
+  for (int j = 0; j < a.k; ++j) {
+    // lane-local best among remaining
+    uint32_t bk = 0u; int64_t bo = INT64_MAX; int bsrc = -1;
+    for (int e = lane; e < E; e += 32) {
+      const int l = e / a.k, jj = e % a.k;
+      const int64_t src = ((int64_t)l * a.nq + q) * a.k + jj;
+      const int64_t off = a.labels[src];
+      if (off < 0) continue;
+      const uint32_t key = float_key(a.ip[src]) | 0u;
+      // remaining iff (key, off) is worse than the last emitted
+      const bool remaining = (j == 0) || key < last_key || (key == last_key && off > last_off);
+      if (!remaining) continue;
+      if (key > bk || (key == bk && off < bo) || bsrc < 0) { bk = key; bo = off; bsrc = (int)src; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int64_t oo = __shfl_xor_sync(0xffffffffu, bo, o);
+      const int os = __shfl_xor_sync(0xffffffffu, bsrc, o);
+      const bool take = os >= 0 && (bsrc < 0 || ok > bk || (ok == bk && oo < bo));
+      if (take) { bk = ok; bo = oo; bsrc = os; }
+    }
+    if (lane == 0) {
+      float ip = -3.402823466e38f, dist = 3.402823466e38f;
+      int64_t lab = -1;
+      if (bsrc >= 0) { ip = a.ip[bsrc]; dist = a.dist[bsrc]; lab = bo; }
+      if (a.out_ip) a.out_ip[(int64_t)q * a.k + j] = ip;
+      a.out_dist[(int64_t)q * a.k + j] = dist;
+      a.out_labels[(int64_t)q * a.k + j] = lab;
+    }
+    if (bsrc < 0) { last_key = 0u; last_off = INT64_MAX; }
+    else { last_key = bk; last_off = bo; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
+  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint32_t);
+  if (smem > 200 * 1024) { set_error("select: too many partial lists (%d)", a.n_lists); return B2K_E_INVALID; }
+  if (smem > 48 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_kernel<<<nq, kSelThreads, smem, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_rerank(const RerankArgs& a, int n_sm, cudaStream_t st) {
+  int bpq = (8 * n_sm + a.nq - 1) / a.nq;
+  if (bpq < 1) bpq = 1;
+  if (bpq > 128) bpq = 128;
+  dim3 grid(bpq, a.nq);
+  rerank_kernel<<<grid, 256, 0, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)a.cand_cap * sizeof(uint64_t);
+  if (smem > 48 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<<<a.nq, kSelThreads, smem, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_merge(const MergeArgs& a, cudaStream_t st) {
+  if (a.nq <= 0) return 0;
+  merge_kernel<<<(a.nq + 3) / 4, 128, 0, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace b2k

@@ -38,7 +38,7 @@ typedef struct b2k_index b2k_index;
 
 /* b2k_set_option keys */
 #define B2K_OPT_PATH          1  /* 0 auto, 1 = K-scan (CUDA-core stream), 2 = K-score (tcgen05 GEMM) */
-#define B2K_OPT_RERANK        2  /* candidates re-ranked in fp32 per query (C'), 32..1024, default 64   */
+#define B2K_OPT_RERANK        2  /* re-rank candidate slots per query, 32..8192, default 1024             */
 #define B2K_OPT_FORCE_EXACT   3  /* 1 = treat every query as uncertified (exercise the exact fp32 scan) */
 #define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 4)    */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
@@ -46,12 +46,15 @@ typedef struct b2k_index b2k_index;
 typedef struct b2k_stats {
   int32_t path;            /* 1 = K-scan, 2 = K-score for the last search                    */
   int32_t n_splits;        /* DB splits (partial lists) per query                            */
-  int32_t n_rerank;        /* C' used                                                        */
+  int32_t n_rerank;        /* candidate slots per query                                      */
   int32_t n_uncertified;   /* queries whose certificate failed -> served by exact fp32 scan  */
   float   eps_max;         /* largest certificate slack used (bound on |bf16 score - exact|) */
   float   err_max;         /* max_row ||bf16(x) - x||_2 over the shard                       */
   float   norm_max;        /* max_row ||x||_2 over the shard                                 */
   int32_t launches;        /* kernels launched by the last search                            */
+  float   score_ms;        /* device time of the scoring kernel(s) of the last pass (CUDA     */
+                           /* events on the launching stream; the roofline numerator's clock) */
+  float   tail_ms;         /* device time of select + rerank + finalize + exact of that pass  */
 } b2k_stats;
 
 typedef struct b2k_synth {
@@ -72,6 +75,10 @@ int         b2k_device_count(int32_t* n);
 int b2k_create(const int32_t* table_dims, int32_t n_tables, int64_t capacity_rows,
                int32_t device, int64_t base_offset, b2k_index** out);
 void b2k_destroy(b2k_index* idx);
+/* faiss indexes grow on add(); this store is sized explicitly.  Re-allocates the shard for
+ * capacity_rows >= ntotal and moves the rows device-to-device (bits unchanged). */
+int b2k_reserve(b2k_index* idx, int64_t capacity_rows);
+int64_t b2k_capacity(const b2k_index* idx);
 
 /* Replaces index.add(arr) (main/create_index.py:311) fused with the per-row
  * np.concatenate of _process_batch (main/create_index.py:176-188): host_tables[t] is a

