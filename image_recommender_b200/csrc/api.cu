@@ -27,7 +27,7 @@ namespace {
 
 constexpr int64_t kStageRows = 16384;     // rows per host->device staging chunk of add()/load()
 constexpr int kMaxNqPerPass = 16384;      // queries per pipeline pass (workspace sizing)
-constexpr int kDefaultCandCap = 1024;
+constexpr int kDefaultCandCap = 0;      // 0: every listed entry can be a candidate (no overflow)
 
 struct DeviceGuard {
   int prev = -1;
@@ -94,7 +94,7 @@ struct b2k_index {
   const void* tmap_q_ptr = nullptr; int tmap_q_rows = 0;
   const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
   // options
-  int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 4, opt_splits = 0;
+  int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 1, opt_splits = 0;
   b2k_stats stats;
   int32_t* h_fail = nullptr;                  // pinned
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // before scoring, after scoring, after the tail
@@ -133,7 +133,8 @@ int ensure_workspace(b2k_index* ix, int nq) {
   const int tc_lists = ix->n_sm;
   const int n_lists = std::max(scan_lists, tc_lists);
   const int exact_splits = exact_num_splits(ix->n_sm);
-  if (nq <= w.nq_cap && w.n_lists == n_lists && w.cand_cap == ix->opt_cand_cap) return 0;
+  const int cand_cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : n_lists * kList;
+  if (nq <= w.nq_cap && w.n_lists == n_lists && w.cand_cap == cand_cap) return 0;
   B2K_CUDA(cudaStreamSynchronize(ix->stream));
   w.release();
   const int cap = std::max(nq, 8);
@@ -146,8 +147,8 @@ int ensure_workspace(b2k_index* ix, int nq) {
   if ((rc = dev_alloc(&w.eps_tc, cap))) return rc;
   if ((rc = dev_alloc(&w.thr, cap))) return rc;
   if ((rc = dev_alloc(&w.partial, (size_t)cap * n_lists * kList))) return rc;
-  if ((rc = dev_alloc(&w.cand_rows, (size_t)cap * ix->opt_cand_cap))) return rc;
-  if ((rc = dev_alloc(&w.cand_ip, (size_t)cap * ix->opt_cand_cap))) return rc;
+  if ((rc = dev_alloc(&w.cand_rows, (size_t)cap * cand_cap))) return rc;
+  if ((rc = dev_alloc(&w.cand_ip, (size_t)cap * cand_cap))) return rc;
   if ((rc = dev_alloc(&w.cand_count, cap))) return rc;
   if ((rc = dev_alloc(&w.flags, cap))) return rc;
   if ((rc = dev_alloc(&w.fail_count, 1))) return rc;
@@ -156,7 +157,7 @@ int ensure_workspace(b2k_index* ix, int nq) {
   if ((rc = dev_alloc(&w.out_ip, (size_t)cap * B2K_MAX_K))) return rc;
   if ((rc = dev_alloc(&w.out_dist, (size_t)cap * B2K_MAX_K))) return rc;
   if ((rc = dev_alloc(&w.out_labels, (size_t)cap * B2K_MAX_K))) return rc;
-  w.nq_cap = cap; w.n_lists = n_lists; w.cand_cap = ix->opt_cand_cap; w.exact_splits = exact_splits;
+  w.nq_cap = cap; w.n_lists = n_lists; w.cand_cap = cand_cap; w.exact_splits = exact_splits;
   ix->tmap_q_ptr = nullptr;   // q_bf16 moved
   return 0;
 }
@@ -411,7 +412,7 @@ int b2k_add_device(b2k_index* ix, const float* const* dev_tables, int64_t n, voi
   PackArgs a;
   fill_pack_args(ix, a, n, ix->ntotal, 1);
   for (int t = 0; t < ix->n_tables; ++t) a.tables[t] = dev_tables[t];
-  int rc = launch_pack(a, stream ? (cudaStream_t)stream : ix->stream);
+  int rc = launch_pack(a, (cudaStream_t)stream);
   if (rc) return rc;
   ix->ntotal += n;
   return 0;
@@ -452,7 +453,7 @@ int b2k_search_device(b2k_index* ix, const float* q_dev, int32_t nq, int32_t k, 
   int rc = check_search_args(ix, q_dev, nq, k, dist_dev, labels_dev);
   if (rc) return rc;
   DeviceGuard g(ix->device);
-  cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+  cudaStream_t st = (cudaStream_t)stream;      // NULL = the legacy default stream, as given
   rc = ensure_workspace(ix, std::min(nq, kMaxNqPerPass));
   if (rc) return rc;
   for (int q0 = 0; q0 < nq; q0 += kMaxNqPerPass) {
@@ -534,7 +535,7 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
       if (value < 0 || value > 2) break;
       ix->opt_path = (int)value; return 0;
     case B2K_OPT_RERANK:
-      if (value < 32 || value > 8192) break;
+      if (value != 0 && (value < 32 || value > 8192)) break;
       ix->opt_cand_cap = (int)value; return 0;
     case B2K_OPT_FORCE_EXACT:
       ix->opt_force_exact = value != 0; return 0;
@@ -732,7 +733,7 @@ int b2k_synth_queries_device(b2k_index* ix, int32_t nq, const b2k_synth* p, uint
   DeviceGuard g(ix->device);
   int rc = ensure_stage(ix);
   if (rc) return rc;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+  cudaStream_t st = (cudaStream_t)stream;
   SynthArgs s;
   fill_synth_args(ix, s, p);
   s.query_mode = 1; s.n = nq; s.first = 0; s.qseed = qseed; s.sigma_q = sigma_q;

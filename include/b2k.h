@@ -38,9 +38,10 @@ typedef struct b2k_index b2k_index;
 
 /* b2k_set_option keys */
 #define B2K_OPT_PATH          1  /* 0 auto, 1 = K-scan (CUDA-core stream), 2 = K-score (tcgen05 GEMM) */
-#define B2K_OPT_RERANK        2  /* re-rank candidate slots per query, 32..8192, default 1024             */
+#define B2K_OPT_RERANK        2  /* re-rank candidate slots per query: 0 = every listed entry (default),  */
+                                 /* else 32..8192 (overflowing queries take the exact fp32 scan)          */
 #define B2K_OPT_FORCE_EXACT   3  /* 1 = treat every query as uncertified (exercise the exact fp32 scan) */
-#define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 4)    */
+#define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 1)    */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
 
 typedef struct b2k_stats {
@@ -102,7 +103,8 @@ int64_t b2k_base_offset(const b2k_index* idx);
 int b2k_search(b2k_index* idx, const float* q_host, int32_t nq, int32_t k,
                float* dist_host, int64_t* labels_host, float* ip_host);
 /* Device-resident variant: q_dev/outputs are device pointers, work is enqueued on
- * `stream` and NOT synchronised. */
+ * `stream` (cudaStream_t as void*; NULL = the legacy default stream) and NOT synchronised.
+ * The index owns one search workspace: use one stream at a time per index. */
 int b2k_search_device(b2k_index* idx, const float* q_dev, int32_t nq, int32_t k,
                       float* dist_dev, int64_t* labels_dev, float* ip_dev, void* stream);
 int b2k_get_stats(b2k_index* idx, b2k_stats* out);   /* synchronises the last search */

@@ -131,7 +131,7 @@ def test_search_auto_path_and_fallback_tc(db20k):
     ix, pk, n = db20k
     ix.set_option(_capi.OPT_PATH, 0)
     q = oracle.synth_queries(DIMS, 9, n, n_clusters=8, qseed=99)
-    assert _check(ix, pk, q[:2], 10)["path"] == 1
+    assert _check(ix, pk, q[:1], 10)["path"] == 1
     assert _check(ix, pk, q, 10)["path"] == 2
     # exhaustive fp32 scan (the route of uncertified queries) returns the same bits
     ix.set_option(_capi.OPT_FORCE_EXACT, 1)
@@ -150,7 +150,7 @@ def test_search_tight_candidate_budget_falls_back_tc(db20k):
         ix.set_option(_capi.OPT_PATH, path)
         st = _check(ix, pk, q, 10)
     assert st["n_uncertified"] > 0
-    ix.set_option(_capi.OPT_RERANK, 1024)
+    ix.set_option(_capi.OPT_RERANK, 0)
     ix.set_option(_capi.OPT_PATH, 0)
 
 
