@@ -90,9 +90,10 @@ struct b2k_index {
   float* stage_rows_f32 = nullptr;            // device staging of packed rows (load)
   Workspace ws;
   // TMA descriptors (host copies; passed by value at launch)
-  alignas(64) CUtensorMap tmap_q, tmap_db;
+  alignas(64) CUtensorMap tmap_q, tmap_db, tmap_db2;   // tmap_db2: 128-row boxes for the CTA-pair kernel
   const void* tmap_q_ptr = nullptr; int tmap_q_rows = 0;
   const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
+  int opt_pair = -1;                          // -1 auto (nq > 128), 0 never, 1 always
   // options
   int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 1, opt_splits = 0;
   b2k_stats stats;
@@ -138,7 +139,7 @@ int ensure_workspace(b2k_index* ix, int nq) {
   B2K_CUDA(cudaStreamSynchronize(ix->stream));
   w.release();
   const int cap = std::max(nq, 8);
-  const int nq_pad = (cap + 127) / 128 * 128;
+  const int nq_pad = (cap + 255) / 256 * 256;
   int rc = 0;
   if ((rc = dev_alloc(&w.q, (size_t)cap * ix->D))) return rc;
   if ((rc = dev_alloc(&w.q_bf16, (size_t)nq_pad * ix->Dp))) return rc;
@@ -167,7 +168,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
                 float* ip_dev, cudaStream_t st) {
   Workspace& w = ix->ws;
   int launches = 0;
-  const int nq_pad = (nq + 127) / 128 * 128;
+  const int nq_pad = (nq + 255) / 256 * 256;
 
   QueryPrepArgs qp;
   qp.q = q_dev; qp.q_bf16 = w.q_bf16; qp.qn2 = w.qn2; qp.eps_scan = w.eps_scan; qp.eps_tc = w.eps_tc;
@@ -202,6 +203,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   } else {
     if (ix->tmap_db_ptr != ix->bf16 || ix->tmap_db_rows != ix->ntotal) {
       rc = score_tc_encode_maps(nullptr, &ix->tmap_db, nullptr, 0, ix->bf16, ix->ntotal, ix->Dp);
+      if (!rc) rc = score_tc2_encode_db_map(&ix->tmap_db2, ix->bf16, ix->ntotal, ix->Dp);
       if (rc) return rc;
       ix->tmap_db_ptr = ix->bf16; ix->tmap_db_rows = ix->ntotal;
     }
@@ -210,13 +212,17 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
       if (rc) return rc;
       ix->tmap_q_ptr = w.q_bf16; ix->tmap_q_rows = nq_pad;
     }
+    const bool pair = ix->opt_pair < 0 ? nq > 128 : ix->opt_pair != 0;
+    const int forced = std::min(ix->opt_splits, w.n_lists);
     ScoreTcArgs ta;
-    ta.tmap_q = &ix->tmap_q; ta.tmap_db = &ix->tmap_db; ta.n_rows = ix->ntotal; ta.Dp = ix->Dp; ta.nq = nq;
-    ta.plan = score_tc_plan(nq, ix->ntotal, ix->n_sm, std::min(ix->opt_splits, w.n_lists));
+    ta.tmap_q = &ix->tmap_q; ta.tmap_db = pair ? &ix->tmap_db2 : &ix->tmap_db;
+    ta.n_rows = ix->ntotal; ta.Dp = ix->Dp; ta.nq = nq;
+    ta.plan = pair ? score_tc2_plan(nq, ix->ntotal, ix->n_sm, forced) : score_tc_plan(nq, ix->ntotal, ix->n_sm, forced);
     ta.partial = w.partial; ta.n_lists = w.n_lists;
-    rc = launch_score_tc(ta, st);
+    rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
     if (rc) return rc;
     ++launches;
+    path = pair ? 3 : 2;
     n_lists_used = ta.plan.n_splits;
     eps = w.eps_tc;
   }
@@ -545,6 +551,9 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
     case B2K_OPT_SPLITS:
       if (value < 0 || value > 4096) break;
       ix->opt_splits = (int)value; return 0;
+    case B2K_OPT_TC_PAIR:
+      if (value < -1 || value > 1) break;
+      ix->opt_pair = (int)value; return 0;
     default: break;
   }
   set_error("set_option: key %d value %lld rejected", key, (long long)value);

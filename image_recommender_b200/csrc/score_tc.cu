@@ -13,58 +13,19 @@
 //   warps 2-5 epilogue: tcgen05.ld 32x32b (thread = query row, 32 DB columns per load),
 //            per-thread threshold filter, per-thread top-32 list in shared memory
 // Pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), all mbarrier.
-#include <cuda.h>
-#include "common.cuh"
-#include "kernels.h"
-#include "ptx.cuh"
+#include "tc_common.cuh"
 
 namespace b2k {
 
-namespace {
+using namespace tc;
 
-constexpr int kBlockM = 128;           // queries per CTA (TMEM lanes)
-constexpr int kBlockN = 256;           // DB rows per accumulator (TMEM columns)
-constexpr int kBlockK = 64;            // bf16 elements per K-block = one 128-byte swizzle row
-constexpr int kUmmaK = 16;
+namespace {
 constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kListBytes = kList * kBlockM * 8;  // scores + rows
-constexpr int kThreads = 192;
-constexpr int kTmemCols = 512;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kListBytes + 256;
-
-// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);      // start address  [0,14)
-  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for SW128 K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-  return d;
-}
-
-// Instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
-                            ((uint32_t)(kBlockM >> 4) << 24);
-
-// Replace the worst entry (slot min_e) of a per-thread list and rescan for the new worst.
-// Returns (new worst slot << 32) | bits(new worst score); the score is the admission threshold.
-__device__ __noinline__ uint64_t list_insert(float* my_s, int32_t* my_r, int min_e, float sc, int32_t row) {
-  my_s[min_e * kBlockM] = sc;
-  my_r[min_e * kBlockM] = row;
-  float mn = INFINITY;
-  int me = 0;
-#pragma unroll
-  for (int e = 0; e < kList; ++e) {
-    const float se = my_s[e * kBlockM];
-    if (se < mn) { mn = se; me = e; }
-  }
-  return ((uint64_t)(uint32_t)me << 32) | (uint64_t)__float_as_uint(mn);
-}
-
+constexpr uint32_t kIdesc = make_idesc(kBlockM, kBlockN);
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -166,36 +127,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
-#pragma unroll 1
-      for (int c = 0; c < kBlockN / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        ptx::tmem_ld_wait();
-        float mx = -INFINITY;
-        const int nvalid = valid - c * 32;           // columns of this chunk that are real rows
-        if (nvalid >= 32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j >= nvalid) v[j] = 0xff800000u;     // -inf: never inserted
-            mx = fmaxf(mx, __uint_as_float(v[j]));
-          }
-        }
-        if (mx > thr) {
-          // rare after warm-up; statically indexed so v[] stays in registers
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sc = __uint_as_float(v[j]);
-            if (sc > thr) {
-              const uint64_t r = list_insert(my_s, my_r, min_e, sc, (int32_t)(row0 + c * 32 + j));
-              thr = __uint_as_float((uint32_t)r);
-              min_e = (int)(r >> 32);
-            }
-          }
-        }
-      }
+      drain_accumulator(taddr, row0, valid, my_s, my_r, thr, min_e);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -247,7 +179,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+}  // namespace
+
+int tc::encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return B2K_E_NODEVICE; }
   cuuint64_t gdim[2] = {cols, rows};
@@ -260,7 +194,6 @@ int encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, 
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return B2K_E_INVALID; }
   return 0;
 }
-}  // namespace
 
 int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_bf16, int nq_pad,
                          const uint16_t* db_bf16, int64_t n_rows, int Dp) {

@@ -1,0 +1,182 @@
+// K-score, CTA-pair version (tcgen05 cta_group::2): the large-batch scoring kernel.
+//
+// Same contract as score_tc.cu (S = Q · Xᵀ in bf16 on the tensor cores, running top-32 per
+// (query, DB split) fused into the epilogue; replaces the contraction of index.search,
+// main/search_from_image.py:247), but two CTAs of one TPC cooperate on a 256-query x 256-row tile:
+//   * each CTA stages ITS 128 queries (A, 16 KB) and HALF of the DB tile (B, 128 rows, 16 KB) per
+//     K-block, so a stage is 32 KB instead of 48 KB: 6 stages fit and the L2 -> SM traffic per
+//     flop drops by a third (the single-CTA kernel is L2-bandwidth bound, profiles/r01_*);
+//   * the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 M=256 N=256 K=16; the
+//     hardware reads A/B from both CTAs' shared memory and writes each CTA's 128 accumulator
+//     rows into that CTA's TMEM;
+//   * TMA loads of both CTAs complete on the LEADER's full barrier; tcgen05.commit multicasts the
+//     "stage free" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both CTAs
+//     arrive remotely on the leader's "accumulator drained" barrier.
+#include "tc_common.cuh"
+
+namespace b2k {
+
+using namespace tc;
+
+namespace {
+constexpr int kStages2 = 6;
+constexpr int kABytes2 = kBlockM * kBlockK * 2;          // 16 KB: this CTA's 128 queries
+constexpr int kBHalfRows = kBlockN / 2;                  // 128 DB rows staged per CTA
+constexpr int kBBytes2 = kBHalfRows * kBlockK * 2;       // 16 KB
+constexpr int kStageBytes2 = kABytes2 + kBBytes2;        // 32 KB per CTA
+constexpr size_t kSmemBytes2 = 1024 + (size_t)kStages2 * kStageBytes2 + kListBytes + 256;
+constexpr uint32_t kIdesc2 = make_idesc(2 * kBlockM, kBlockN);   // M=256 across the pair
+}  // namespace
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                 int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
+                 int32_t n_lists, Cand* __restrict__ partial) {
+  extern __shared__ unsigned char smem_raw[];
+  // identical carve-up in both CTAs: the MMA and the multicast commits address the peer by offset
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* ring = smem;
+  float* lscore = reinterpret_cast<float*>(smem + (size_t)kStages2 * kStageBytes2);   // [32][128]
+  int32_t* lrow = reinterpret_cast<int32_t*>(lscore + kList * kBlockM);
+  uint64_t* full = reinterpret_cast<uint64_t*>(lrow + kList * kBlockM);   // used in the leader only
+  uint64_t* empty = full + kStages2;
+  uint64_t* tfull = empty + kStages2;     // [2]
+  uint64_t* tempty = tfull + 2;           // [2] used in the leader only
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int qtile = pair % n_qtiles;                     // 256 queries per pair
+  const int split = pair / n_qtiles;
+  const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
+  const int64_t tile_begin = tiles_total * split / n_splits;
+  const int64_t tile_end = tiles_total * (split + 1) / n_splits;
+  const int n_tiles = (int)(tile_end - tile_begin);
+  const int q_row0 = qtile * 2 * kBlockM + (int)rank * kBlockM;   // first query of this CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages2; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 8); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { ptx::tma_prefetch_desc(&tmap_q); ptx::tma_prefetch_desc(&tmap_db); }
+  if (warp == 1) { ptx::tmem_alloc_pair(tmem_base_slot, kTmemCols); ptx::tmem_relinquish_pair(); }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();               // barriers of both CTAs initialised, TMEM allocated
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int32_t row0 = (int32_t)((tile_begin + t) * kBlockN) + (int32_t)rank * kBHalfRows;
+        for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+          const int s = it % kStages2;
+          ptx::mbar_wait(&empty[s], ((it / kStages2) & 1) ^ 1);
+          unsigned char* a_dst = ring + (size_t)s * kStageBytes2;
+          unsigned char* b_dst = a_dst + kABytes2;
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kStageBytes2);   // bytes of both CTAs
+          ptx::tma_load_2d_pair(a_dst, &tmap_q, kb * kBlockK, q_row0, &full[s], ptx::kEvictLast);
+          ptx::tma_load_2d_pair(b_dst, &tmap_db, kb * kBlockK, row0, &full[s], ptx::kEvictNormal);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader only) ------------------------------
+    if (rank == 0) {
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int acc = t & 1;
+        ptx::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBlockN);
+        for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+          const int s = it % kStages2;
+          ptx::mbar_wait(&full[s], (it / kStages2) & 1);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * kStageBytes2);
+            const uint64_t a_desc = make_sw128_desc(a_addr);
+            const uint64_t b_desc = make_sw128_desc(a_addr + kABytes2);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              ptx::umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc2,
+                                  (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit_pair(&empty[s], 3);                        // stage free in both CTAs
+            if (kb == n_kblocks - 1) ptx::umma_commit_pair(&tfull[acc], 3);   // accumulators ready in both
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs) ------------------------------
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int qi = q_row0 + m;
+    float* my_s = lscore + m;
+    int32_t* my_r = lrow + m;
+#pragma unroll
+    for (int e = 0; e < kList; ++e) { my_s[e * kBlockM] = -INFINITY; my_r[e * kBlockM] = -1; }
+    float thr = -INFINITY;
+    int min_e = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = t & 1;
+      const int64_t row0 = (tile_begin + t) * kBlockN;
+      const int valid = (int)min((int64_t)kBlockN, n_rows - row0);
+      ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
+      drain_accumulator(taddr, row0, valid, my_s, my_r, thr, min_e);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote(&tempty[acc], 0);          // the leader's barrier
+    }
+    if (qi < nq) {
+      Cand* out = partial + ((int64_t)qi * n_lists + split) * kList;
+#pragma unroll 4
+      for (int e = 0; e < kList; ++e) {
+        Cand c; c.score = my_s[e * kBlockM]; c.row = my_r[e * kBlockM];
+        out[e] = c;
+      }
+    }
+  }
+
+  // neither CTA may exit (or free TMEM) while its peer can still touch its shared memory
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_pair(tmem_base, kTmemCols); }
+}
+
+// ---------------------------------------------------------------------------------------
+ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) {
+  ScoreTcPlan p;
+  p.n_qtiles = (nq + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
+  int splits = forced_splits > 0 ? forced_splits : n_sm;
+  if ((int64_t)splits > tiles_total) splits = (int)(tiles_total > 0 ? tiles_total : 1);
+  p.n_splits = splits;
+  p.grid = 2 * p.n_qtiles * p.n_splits;
+  return p;
+}
+
+int score_tc2_encode_db_map(void* tmap_db_out, const uint16_t* db_bf16, int64_t n_rows, int Dp) {
+  return encode_2d(reinterpret_cast<CUtensorMap*>(tmap_db_out), db_bf16, (uint64_t)n_rows, (uint64_t)Dp, kBHalfRows);
+}
+
+int launch_score_tc2(const ScoreTcArgs& a, cudaStream_t st) {
+  B2K_CUDA(cudaFuncSetAttribute(score_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
+  const CUtensorMap* mq = reinterpret_cast<const CUtensorMap*>(a.tmap_q);
+  const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(a.tmap_db);
+  score_tc2_kernel<<<a.plan.grid, kThreads, kSmemBytes2, st>>>(*mq, *md, a.n_rows, a.Dp / kBlockK, a.nq,
+                                                              a.plan.n_qtiles, a.plan.n_splits, a.n_lists,
+                                                              a.partial);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace b2k

@@ -1,0 +1,88 @@
+// Pieces shared by the tcgen05 scoring kernels (score_tc.cu: one CTA per tile, score_tc2.cu: CTA pairs).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b2k { namespace tc {
+
+constexpr int kBlockM = 128;           // queries per CTA (TMEM lanes)
+constexpr int kBlockN = 256;           // DB rows per accumulator (TMEM columns)
+constexpr int kBlockK = 64;            // bf16 elements per K-block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kTmemCols = 512;         // two 128 x 256 fp32 accumulators
+constexpr int kListBytes = kList * kBlockM * 8;  // per-thread top-32 lists: scores + rows
+constexpr int kThreads = 192;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);      // start address  [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor: D=f32, A=B=bf16, both K-major.
+constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Replace the worst entry (slot min_e) of a per-thread list and rescan for the new worst.
+// Returns (new worst slot << 32) | bits(new worst score); the score is the admission threshold.
+static __device__ __noinline__ uint64_t list_insert(float* my_s, int32_t* my_r, int min_e, float sc, int32_t row) {
+  my_s[min_e * kBlockM] = sc;
+  my_r[min_e * kBlockM] = row;
+  float mn = INFINITY;
+  int me = 0;
+#pragma unroll
+  for (int e = 0; e < kList; ++e) {
+    const float se = my_s[e * kBlockM];
+    if (se < mn) { mn = se; me = e; }
+  }
+  return ((uint64_t)(uint32_t)me << 32) | (uint64_t)__float_as_uint(mn);
+}
+
+// Drain one 128 x 256 accumulator: this thread owns TMEM lane (= query row) `taddr`'s lane field and
+// filters the 256 scores of DB rows row0 .. row0+255 (only the first `valid` are real rows)
+// against its running threshold.
+__device__ __forceinline__ void drain_accumulator(uint32_t taddr, int64_t row0, int valid, float* my_s,
+                                                  int32_t* my_r, float& thr, int& min_e) {
+#pragma unroll 1
+  for (int c = 0; c < kBlockN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+    ptx::tmem_ld_wait();
+    float mx = -INFINITY;
+    const int nvalid = valid - c * 32;           // columns of this chunk that are real rows
+    if (nvalid >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j >= nvalid) v[j] = 0xff800000u;     // -inf: never inserted
+        mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+    }
+    if (mx > thr) {
+      // rare after warm-up; statically indexed so v[] stays in registers
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float sc = __uint_as_float(v[j]);
+        if (sc > thr) {
+          const uint64_t r = list_insert(my_s, my_r, min_e, sc, (int32_t)(row0 + c * 32 + j));
+          thr = __uint_as_float((uint32_t)r);
+          min_e = (int)(r >> 32);
+        }
+      }
+    }
+  }
+}
+
+int encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+}}  // namespace b2k::tc

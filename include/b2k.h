@@ -43,9 +43,10 @@ typedef struct b2k_index b2k_index;
 #define B2K_OPT_FORCE_EXACT   3  /* 1 = treat every query as uncertified (exercise the exact fp32 scan) */
 #define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 1)    */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
+#define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs when nq > 128), 0 single CTA, 1 pairs */
 
 typedef struct b2k_stats {
-  int32_t path;            /* 1 = K-scan, 2 = K-score for the last search                    */
+  int32_t path;            /* last search: 1 = K-scan, 2 = K-score (1 CTA), 3 = K-score (CTA pairs) */
   int32_t n_splits;        /* DB splits (partial lists) per query                            */
   int32_t n_rerank;        /* candidate slots per query                                      */
   int32_t n_uncertified;   /* queries whose certificate failed -> served by exact fp32 scan  */

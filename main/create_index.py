@@ -1,0 +1,290 @@
+"""Index build for the retrieval hot path — drop-in for the reference's main/create_index.py.
+
+Same class, constructor kwargs, method names, SQLite schema and offset table as the reference
+(`FAISSIndexBuilderDB`, /root/reference/main/create_index.py:13-325); the FAISS HNSW / IVFPQ
+index is replaced by an exact flat store on the GPU (`image_recommender_b200.FlatShard`):
+rows are per-table L2-normalised, concatenated and bf16-packed by a CUDA kernel as they are
+added.  There is no CPU path: without a B200 the build raises.
+
+CLI (README.md:101-105 of the reference; the reference itself hard-codes its parameters):
+
+    python -m main.create_index --db-path images.db --vector-types color sift dreamsim \
+        --output index_hnsw.faiss [--batch-size 8192] [--hnsw_M 32] [--efConstruction 200] [--efSearch 64]
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import pickle
+import sqlite3
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+from image_recommender_b200 import FlatShard  # noqa: E402  (raises if the CUDA extension is missing)
+
+
+class FAISSIndexBuilderDB:
+    def __init__(
+        self,
+        db_path: str = "images.db",
+        vector_types: list = None,
+        batch_size: int = 8192,
+        index_file: str = None,
+        hnsw_M: int = 32,
+        efConstruction: int = 200,
+        efSearch: int = 64,
+        log_file: str = "faiss_builder.log",
+        log_dir: str = "logs",
+        device: int = 0,
+    ):
+        # reference: create_index.py:14-53 (same attribute names; `device` is new)
+        self.log_dir = log_dir
+        self.log_file = log_file
+        self._setup_logging()
+
+        self.db_path = db_path
+        if not vector_types:
+            raise TypeError("vector_types must be a non-empty list, e.g. ['color', 'sift', 'dreamsim']")
+        self.vector_types = list(vector_types)
+        self.vector_cols = [f"{t}_vector_blob" for t in self.vector_types]
+        self.batch_size = batch_size
+
+        name = "_".join(self.vector_types)
+        self.index_file = Path(index_file) if index_file else Path(f"index_hnsw_{name}.faiss")
+
+        # accepted for API compatibility; exact search has no graph to tune
+        self.hnsw_M = hnsw_M
+        self.efConstruction = efConstruction
+        self.efSearch = efSearch
+        self.device = device
+
+        self.offset_table = f"faiss_index_offsets_{name}"
+
+        self.read_conn = sqlite3.connect(self.db_path)
+        self._configure_db(self.read_conn)
+        self.read_cur = self.read_conn.cursor()
+
+        self.write_conn = sqlite3.connect(self.db_path)
+        self._configure_db(self.write_conn)
+        self.write_cur = self.write_conn.cursor()
+
+        self._prepare_offset_table()
+
+    # ---- logging (create_index.py:55-87) ---------------------------------------------------
+    def _setup_logging(self):
+        Path(self.log_dir).mkdir(parents=True, exist_ok=True)
+        full_path = Path(self.log_dir) / self.log_file
+        logging.basicConfig(
+            level=logging.INFO,
+            filename=str(full_path),
+            filemode="a",
+            format="%(asctime)s - %(levelname)s - %(message)s",
+            encoding="utf-8",
+        )
+        self._log(f"Logging initialized (file={full_path})", level="info")
+
+    def _log(self, message: str, level: str = "info"):
+        print(message)
+        getattr(logging, {"info": "info", "warning": "warning", "error": "error"}.get(level.lower(), "debug"))(message)
+
+    # ---- SQLite (create_index.py:89-158) ------------------------------------------------------
+    def _configure_db(self, conn):
+        conn.execute("PRAGMA journal_mode=WAL;")
+        conn.execute("PRAGMA synchronous=OFF;")
+
+    def _prepare_offset_table(self):
+        self.write_cur.execute(
+            f"""
+            CREATE TABLE IF NOT EXISTS {self.offset_table} (
+                image_id INTEGER PRIMARY KEY,
+                offset   INTEGER
+            );
+            """
+        )
+        # new: the reference looks hits up with an unindexed `WHERE offset = ?` (F7)
+        self.write_cur.execute(
+            f"CREATE INDEX IF NOT EXISTS idx_{self.offset_table}_offset ON {self.offset_table} (offset);"
+        )
+        self.write_conn.commit()
+        self._log(f"Offset table '{self.offset_table}' is ready.", level="info")
+
+    def _make_select_and_joins(self):
+        select_cols = ["i.id"]
+        join_strs = []
+        for vtype in self.vector_types:
+            alias = vtype[0]
+            vtable = f"{vtype}_vectors"
+            vcol = f"{vtype}_vector_blob"
+            select_cols.append(f"{alias}.{vcol}")
+            join_strs.append(f"JOIN {vtable} {alias} ON i.id = {alias}.image_id")
+        return ", ".join(select_cols), " ".join(join_strs)
+
+    def _count_records(self):
+        _, join_strs = self._make_select_and_joins()
+        query = f"SELECT COUNT(*) FROM images i {join_strs}"
+        return self.read_cur.execute(query).fetchone()[0]
+
+    def _batch_records(self):
+        select_cols, join_strs = self._make_select_and_joins()
+        query = f"SELECT {select_cols} FROM images i {join_strs}"
+        self.read_cur.execute(query)
+        while True:
+            rows = self.read_cur.fetchmany(self.batch_size)
+            if not rows:
+                break
+            yield rows
+
+    # ---- decode (create_index.py:160-189) -------------------------------------------------------
+    @staticmethod
+    def _decode_blob(blob) -> np.ndarray:
+        vec = pickle.loads(blob)
+        if hasattr(vec, "cpu"):
+            vec = vec.cpu().numpy()
+        return np.asarray(vec, dtype="float32").ravel()
+
+    def _process_batch(self, rows):
+        """Same contract as the reference: (ids, [concatenated float32 row per id]); a row with an
+        undecodable blob is logged and skipped."""
+        ids, parts = self._decode_batch(rows)
+        return ids, [np.concatenate(p) for p in parts]
+
+    def _decode_batch(self, rows):
+        ids, parts_per_row = [], []
+        for rec_id, *blobs in rows:
+            parts = []
+            skip = False
+            for vt, blob in zip(self.vector_types, blobs):
+                try:
+                    parts.append(self._decode_blob(blob))
+                except Exception as e:
+                    self._log(f"ID {rec_id}: error loading {vt}: {e}", level="warning")
+                    skip = True
+                    break
+            if skip:
+                continue
+            ids.append(rec_id)
+            parts_per_row.append(parts)
+        return ids, parts_per_row
+
+    def find_valid_m(self, dim, candidates=(64, 56, 48, 32, 28, 24, 16, 12, 8)):
+        # kept for API compatibility (create_index.py:191-205); product quantisation is not used
+        for m in candidates:
+            if dim % m == 0:
+                return m
+        return 1
+
+    def _initialize_index(self, table_dims, capacity, use_pq=True):
+        """reference: IndexIVFPQ over an HNSW coarse quantiser, or IndexHNSWFlat
+        (create_index.py:207-234).  Here: one exact flat shard; M/efConstruction/efSearch/use_pq
+        are accepted and ignored."""
+        index = FlatShard(list(table_dims), int(capacity), device=self.device)
+        self._log(
+            f"Created exact flat GPU index (dims={list(table_dims)}, D={index.d}, capacity={capacity}; "
+            f"hnsw_M={self.hnsw_M}, efConstruction={self.efConstruction}, efSearch={self.efSearch} ignored)",
+            level="info",
+        )
+        return index
+
+    def _store_offsets(self, ids, start_offset):
+        pairs = [(rid, start_offset + i) for i, rid in enumerate(ids)]
+        self.write_cur.executemany(
+            f"INSERT OR REPLACE INTO {self.offset_table} (image_id, offset) VALUES (?, ?)",
+            pairs,
+        )
+        self.write_conn.commit()
+
+    # ---- build (create_index.py:251-325) ----------------------------------------------------------
+    def build_index(self, update_index: bool = False):
+        """One pass over the joined tables: decode -> per-table arrays -> GPU pack (normalise,
+        concatenate, bf16) -> offsets.  The reference's separate "training" pass
+        (create_index.py:283-299) has no counterpart: nothing is trained.
+
+        update_index=True appends the images that have no offset yet to the existing index file
+        (the reference's flag restarts at offset 0 and is unusable)."""
+        combo = "_".join(self.vector_types)
+        self._log(f"Starting index build for [{combo}]…", level="info")
+
+        index = None
+        all_ids: list[int] = []
+        offset_counter = 0
+        known = set()
+        if update_index and self.index_file.exists():
+            from image_recommender_b200 import file_info, load_ids
+            info = file_info(self.index_file)
+            index = FlatShard.load(self.index_file, device=self.device)
+            offset_counter = index.ntotal
+            if info["has_ids"]:
+                all_ids = load_ids(self.index_file, 0, info["n_rows"]).tolist()
+            known = set(all_ids)
+            self._log(f"Appending to {self.index_file} ({offset_counter} vectors).", level="info")
+        else:
+            if self.index_file.exists():
+                self._log(f"Removing existing index {self.index_file}", level="info")
+                self.index_file.unlink()
+            self._log(f"Clearing offset table {self.offset_table}", level="info")
+            self.write_cur.execute(f"DELETE FROM {self.offset_table}")
+            self.write_conn.commit()
+
+        total = self._count_records()
+        self._log(f"{total} complete records found.", level="info")
+        if total == 0:
+            self._log("No complete embeddings found; aborting.", level="error")
+            return
+
+        batch_num = 0
+        for batch in self._batch_records():
+            batch_num += 1
+            ids, parts = self._decode_batch(batch)
+            if known:
+                keep = [i for i, rid in enumerate(ids) if rid not in known]
+                ids = [ids[i] for i in keep]
+                parts = [parts[i] for i in keep]
+            if not ids:
+                continue
+            tables = [np.stack([p[t] for p in parts]).astype("float32") for t in range(len(self.vector_types))]
+            if index is None:
+                index = self._initialize_index([t.shape[1] for t in tables], total)
+            index.add_tables(tables)
+            self._store_offsets(ids, offset_counter)
+            all_ids.extend(ids)
+            offset_counter += len(ids)
+            self._log(f"Batch {batch_num}: added {len(ids)} vectors (total {offset_counter}).", level="info")
+
+        if index is None:
+            self._log("No decodable embeddings found; aborting.", level="error")
+            return
+        self._log(f"Writing index to {self.index_file.resolve()}", level="info")
+        index.save(self.index_file, np.asarray(all_ids, dtype=np.int64))
+        self._log(f"Index saved ({index.ntotal} vectors).", level="info")
+        index.close()
+
+        self.read_conn.close()
+        self.write_conn.close()
+        self._log("Done.", level="info")
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Build the exact GPU index from the SQLite vector tables")
+    ap.add_argument("--db-path", default="images.db")
+    ap.add_argument("--vector-types", nargs="+", default=["color"], help="any of: color sift dreamsim")
+    ap.add_argument("--output", default=None, help="index file (default index_hnsw_<types>.faiss)")
+    ap.add_argument("--batch-size", type=int, default=8192)
+    ap.add_argument("--hnsw_M", type=int, default=32)
+    ap.add_argument("--efConstruction", type=int, default=200)
+    ap.add_argument("--efSearch", type=int, default=64)
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--update", action="store_true", help="append images that have no offset yet")
+    a = ap.parse_args(argv)
+    builder = FAISSIndexBuilderDB(
+        db_path=a.db_path, vector_types=a.vector_types, batch_size=a.batch_size, index_file=a.output,
+        hnsw_M=a.hnsw_M, efConstruction=a.efConstruction, efSearch=a.efSearch, device=a.device,
+    )
+    builder.build_index(update_index=a.update)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,303 @@
+"""Top-k query for the retrieval hot path — drop-in for the reference's main/search_from_image.py.
+
+`ImageRecommender` keeps the reference's constructor kwargs and method names
+(/root/reference/main/search_from_image.py:17-379); `index.search` runs as exact brute-force
+search on the GPU (`image_recommender_b200.FlatShard`) instead of a FAISS HNSW/IVFPQ walk, the
+index is loaded once and kept resident (the reference re-reads it on every call) and
+`faiss.normalize_L2` is the package's CUDA kernel.  Feature *extraction* (colour histogram,
+SIFT-VLAD, DreamSim inference) is outside this repository's scope: query vectors come from the
+SQLite vector tables exactly as the reference's cache path does (search_from_image.py:50-92).
+
+CLI (README.md:110 of the reference):
+
+    python -m main.search_from_image --db-path images.db --images-root image_data \
+        --query path/to/query.jpg --index combo_color_sift_dreamsim --top-k 5
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import logging
+import pickle
+import sqlite3
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+from image_recommender_b200 import FlatShard, normalize_L2  # noqa: E402
+
+VALID_TYPES = ["color", "hog", "lpips", "dreamsim", "sift", "color_sift", "sift_dreamsim"]
+TABLES = {  # type -> (table, column)   (create_db.py:59-85)
+    "color": ("color_vectors", "color_vector_blob"),
+    "sift": ("sift_vectors", "sift_vector_blob"),
+    "dreamsim": ("dreamsim_vectors", "dreamsim_vector_blob"),
+}
+
+
+class ImageRecommender:
+    def __init__(
+        self,
+        images_root="image_data",
+        db_path="images.db",
+        use_gpu=True,
+        sift_codebook_path="sift_codebook.npy",
+        sift_pca_path="sift_vlad_pca.joblib",
+        sift_n_clusters=256,
+        sift_desc_dim=128,
+        top_k=5,
+        index_dir=".",
+        device=0,
+    ):
+        self.base_dir = Path().expanduser().resolve()
+        self.images_root = (self.base_dir / images_root).resolve()
+        self.db_path = Path(db_path).expanduser().resolve()
+        if not use_gpu:
+            raise ValueError("this engine is GPU-only (no CPU search path); use_gpu=False is not supported")
+        self.use_gpu = use_gpu
+        self.device = device
+        # extractor settings are accepted for signature compatibility only
+        self.sift_codebook_path = Path(sift_codebook_path).expanduser().resolve()
+        self.sift_pca_path = Path(sift_pca_path).expanduser().resolve()
+        self.sift_n_clusters = sift_n_clusters
+        self.sift_desc_dim = sift_desc_dim
+        self.top_k = top_k
+        self.index_dir = Path(index_dir)
+        self._resident = {}      # index file -> (mtime, FlatShard)
+        logging.basicConfig(level=logging.INFO, format="%(asctime)s [%(levelname)s] %(message)s")
+
+    # ---- query-vector acquisition (search_from_image.py:50-216) -------------------------------
+    def _get_db_vector(self, path_rel: str, vector_table: str, vector_column: str):
+        conn = sqlite3.connect(self.db_path)
+        try:
+            cur = conn.cursor()
+            row = cur.execute("SELECT id FROM images WHERE path = ?", (path_rel,)).fetchone()
+            if not row:
+                # create_db.py:99 stores paths relative to the PARENT of the image folder
+                row = cur.execute("SELECT id FROM images WHERE path = ?",
+                                  (f"{self.images_root.name}/{path_rel}",)).fetchone()
+            if not row:
+                return None
+            vrow = cur.execute(f"SELECT {vector_column} FROM {vector_table} WHERE image_id = ?", (row[0],)).fetchone()
+        finally:
+            conn.close()
+        if not vrow or vrow[0] is None:
+            return None
+        blob = vrow[0]
+        try:
+            arr = pickle.loads(blob)
+            if hasattr(arr, "cpu"):
+                arr = arr.cpu().numpy()
+            if isinstance(arr, np.ndarray):
+                return arr.reshape(1, -1) if arr.ndim == 1 else arr
+        except Exception:
+            pass
+        if len(blob) % 4 != 0:       # raw little-endian float32 fallback (search_from_image.py:82-91)
+            logging.warning(f"invalid blob size {len(blob)} B for '{vector_column}' at '{path_rel}', skipping cache")
+            return None
+        return np.frombuffer(blob, dtype="float32").reshape(1, -1)
+
+    def get_or_compute_vector(self, path_rel, vector_table, vector_column, compute_func=None, reshape=None,
+                              print_vectors=False):
+        cached = self._get_db_vector(path_rel, vector_table, vector_column)
+        if cached is not None:
+            return cached
+        vec = compute_func() if compute_func is not None else None
+        if vec is None:
+            logging.error(f"No cached {vector_column} for '{path_rel}' (feature extraction is out of scope here: "
+                          f"run the reference's vector_scripts first).")
+            return None
+        return vec.reshape(*reshape) if reshape is not None else vec
+
+    def extract_color_features(self, path_rel):
+        return self.get_or_compute_vector(path_rel, *TABLES["color"], reshape=(1, -1))
+
+    def extract_sift_vlad_features(self, path_rel):
+        return self.get_or_compute_vector(path_rel, *TABLES["sift"])
+
+    def extract_dreamsim_features(self, path_rel):
+        return self.get_or_compute_vector(path_rel, *TABLES["dreamsim"])
+
+    # ---- main search (search_from_image.py:219-254) ---------------------------------------------
+    def search_similar_images(self, query_image_paths, index_type: str = "color", plot: bool = False):
+        """Returns [(path, squared-L2 distance)] ascending, as the reference's `_fetch_results`
+        (which it then only plots)."""
+        paths_rel = [self._relative(p) for p in query_image_paths]
+        ordered = self._get_ordered_index_types(index_type)
+        if not ordered:
+            return None
+        index, offset_table, file_order = self._load_faiss_index("_".join(ordered), ordered)
+        if index is None:
+            return None
+        query_vec = self._extract_query_vector(paths_rel, file_order)
+        if query_vec is None:
+            return None
+        distances, indices = index.search(query_vec, self.top_k)
+        results = self._fetch_results(indices, distances, offset_table)
+        if not results:
+            logging.error("No similar images found.")
+            return None
+        if plot:
+            self._plot_results(query_image_paths, results)
+        return results
+
+    def search_batch(self, query_groups, index_type: str = "color"):
+        """New: one query vector per group of image paths, searched as one batch."""
+        ordered = self._get_ordered_index_types(index_type)
+        if not ordered:
+            return None
+        index, offset_table, file_order = self._load_faiss_index("_".join(ordered), ordered)
+        if index is None:
+            return None
+        vecs = [self._extract_query_vector([self._relative(p) for p in g], file_order) for g in query_groups]
+        if any(v is None for v in vecs):
+            return None
+        q = np.ascontiguousarray(np.concatenate(vecs, axis=0), dtype=np.float32)
+        distances, indices = index.search(q, self.top_k)
+        return [self._fetch_results(indices[i:i + 1], distances[i:i + 1], offset_table) for i in range(len(vecs))]
+
+    def _relative(self, p):
+        # search_from_image.py:230-232
+        return Path(p).resolve().relative_to(self.images_root).as_posix()
+
+    def _get_ordered_index_types(self, index_type: str):
+        # accepts README's `combo_color_sift_dreamsim` as well as the reference's `color,sift`
+        text = index_type.lower()
+        if text.startswith("combo_"):
+            text = text[len("combo_"):].replace("_", ",")
+        requested = [x.strip() for x in text.split(",")]
+        ordered = [v for v in VALID_TYPES if v in requested]
+        if not ordered:
+            logging.error(f"Unknown index_type '{index_type}'. Choose from {VALID_TYPES}.")
+            return []
+        return ordered
+
+    def _extract_query_vector(self, paths_rel, ordered):
+        all_query_vectors = []
+        for path_rel in paths_rel:
+            parts = []
+            for vec_type in ordered:
+                if vec_type == "color":
+                    parts.append(self.extract_color_features(path_rel))
+                elif vec_type == "sift":
+                    parts.append(self.extract_sift_vlad_features(path_rel))
+                elif vec_type == "dreamsim":
+                    parts.append(self.extract_dreamsim_features(path_rel))
+                else:
+                    logging.error(f"Unknown vector type '{vec_type}' for '{path_rel}'.")
+                    return None
+            if any(p is None for p in parts):
+                logging.error(f"Could not load all vector features for '{path_rel}', skipping this image.")
+                continue
+            parts = [x.reshape(1, -1) if x.ndim == 1 else x for x in parts]
+            all_query_vectors.append(np.concatenate(parts, axis=1).astype("float32"))
+        if not all_query_vectors:
+            logging.error("Could not extract a vector for any of the query images.")
+            return None
+        combined_vec = np.ascontiguousarray(np.mean(all_query_vectors, axis=0), dtype=np.float32)
+        if combined_vec.ndim == 1:
+            combined_vec = combined_vec.reshape(1, -1)
+        normalize_L2(combined_vec, device=self.device)      # faiss.normalize_L2 (search_from_image.py:322)
+        return combined_vec
+
+    def _load_faiss_index(self, canonical, ordered=None):
+        """(index, offset table, concat order of that file).  The reference looks only for
+        index_hnsw_<fixed-order>.faiss, which never matches an index built in another order
+        (SURVEY F6); here every ordering of the requested types is tried, fixed order first."""
+        ordered = ordered or canonical.split("_")
+        candidates = [tuple(ordered)] + [p for p in itertools.permutations(ordered) if p != tuple(ordered)]
+        for order in candidates:
+            name = "_".join(order)
+            f = self.index_dir / f"index_hnsw_{name}.faiss"
+            if not f.exists():
+                continue
+            try:
+                mtime = f.stat().st_mtime
+                hit = self._resident.get(str(f))
+                if hit is None or hit[0] != mtime:
+                    if hit is not None:
+                        hit[1].close()
+                    self._resident[str(f)] = (mtime, FlatShard.load(f, device=self.device))
+                    logging.info(f"Loaded index '{f}' with {self._resident[str(f)][1].ntotal} vectors.")
+                return self._resident[str(f)][1], f"faiss_index_offsets_{name}", list(order)
+            except Exception as e:
+                logging.error(f"Error loading index '{f}': {e}")
+                return None, None, None
+        logging.error(f"Error loading index 'index_hnsw_{canonical}.faiss': no such file in {self.index_dir}")
+        return None, None, None
+
+    def _fetch_results(self, indices, distances, offset_table):
+        conn = sqlite3.connect(self.db_path)
+        cur = conn.cursor()
+        results = []
+        for rank, offset in enumerate(indices[0]):
+            if offset < 0:
+                continue                      # -1 padding when top_k > ntotal
+            row = cur.execute(f"SELECT image_id FROM {offset_table} WHERE offset = ?", (int(offset),)).fetchone()
+            if not row:
+                logging.warning(f"No entry found for offset={offset} in {offset_table}")
+                continue
+            fp_row = cur.execute("SELECT path FROM images WHERE id = ?", (row[0],)).fetchone()
+            if not fp_row:
+                logging.warning(f"No path found for id={row[0]}")
+                continue
+            results.append((Path(self.base_dir) / fp_row[0], float(distances[0, rank])))
+        conn.close()
+        results.sort(key=lambda x: x[1])
+        return results
+
+    def _plot_results(self, query_image_paths, results):
+        """matplotlib display of the reference (search_from_image.py:381-427); optional here."""
+        try:
+            import matplotlib.pyplot as plt
+            from PIL import Image
+        except Exception as e:          # plotting is not part of the hot path
+            logging.warning(f"plotting skipped ({e})")
+            return
+        items = [(p, f"Query: {Path(p).name}") for p in query_image_paths] + \
+                [(fp, f"{Path(fp).name}\nDist: {d:.4f}") for fp, d in results]
+        ncols = max(4, len(query_image_paths))
+        nrows = -(-len(items) // ncols)
+        fig, axes = plt.subplots(nrows, ncols, figsize=(5 * ncols, 5 * nrows))
+        axes = np.atleast_1d(axes).flatten()
+        for ax in axes:
+            ax.axis("off")
+        for ax, (p, title) in zip(axes, items):
+            try:
+                ax.imshow(Image.open(p).convert("RGB"))
+                ax.set_title(title)
+            except Exception as e:
+                logging.error(f"Error rendering {p}: {e}")
+        plt.tight_layout(pad=2.0, h_pad=3.0)
+        plt.show()
+
+    def close(self):
+        for _, ix in self._resident.values():
+            ix.close()
+        self._resident.clear()
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Exact top-k image search on the GPU index")
+    ap.add_argument("--db-path", default="images.db")
+    ap.add_argument("--images-root", default="image_data")
+    ap.add_argument("--query", nargs="+", required=True, help="query image path(s); several are averaged")
+    ap.add_argument("--index", default="color", help="e.g. combo_color_sift_dreamsim or color,sift")
+    ap.add_argument("--top-k", type=int, default=5)
+    ap.add_argument("--index-dir", default=".")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--plot", action="store_true")
+    a = ap.parse_args(argv)
+    rec = ImageRecommender(images_root=a.images_root, db_path=a.db_path, top_k=a.top_k, index_dir=a.index_dir,
+                           device=a.device)
+    results = rec.search_similar_images(a.query, index_type=a.index, plot=a.plot)
+    for fp, dist in results or []:
+        print(f"{dist:.6f}\t{fp}")
+    rec.close()
+    return 0 if results else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 SMALL="--rows 2000000 --batch 1024 --steps 2 --warmup 1 --no-cpu-baseline"
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"score_tc|scan_bf16|select_|rerank_|finalize_|exact_|query_prep|merge_|normalize_" -c 800 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 echo "launch list exit $?"
 python bench.py $SMALL > gpurun_out/plain_small.log 2>&1 &&

@@ -11,7 +11,11 @@ if str(ROOT) not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
     # Build what is missing (nvcc cross-compiles here; on the GPU box the .so files travel).
-    from image_recommender_b200 import build_ext
+    # load the build script by path: importing the package itself requires the built library
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("b2k_build_ext", ROOT / "image_recommender_b200" / "build_ext.py")
+    build_ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build_ext)
     if build_ext.needs_build():
         build_ext.build()
     import oracle

@@ -114,25 +114,39 @@ def _check(ix, pk, q, k, base=0):
     return ix.stats()
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["scan", "tc"])
-@pytest.mark.parametrize("nq,k", [(1, 10), (3, 5), (4, 10), (7, 1), (130, 10), (300, 32)])
+def _set_path(ix, name):
+    """scan = K-scan (CUDA cores); tc = tcgen05 single-CTA tiles; tc2 = tcgen05 CTA pairs."""
+    from image_recommender_b200 import _capi
+    path, pair, want = {"scan": (1, -1, 1), "tc": (2, 0, 2), "tc2": (2, 1, 3), "auto": (0, -1, None)}[name]
+    ix.set_option(_capi.OPT_PATH, path)
+    ix.set_option(_capi.OPT_TC_PAIR, pair)
+    return want
+
+
+@pytest.mark.parametrize("path", ["scan", "tc", "tc2"])
+@pytest.mark.parametrize("nq,k", [(1, 10), (3, 5), (4, 10), (7, 1), (130, 10), (300, 32), (513, 10)])
 def test_search_matches_oracle(db20k, path, nq, k):
     from image_recommender_b200 import _capi
     ix, pk, n = db20k
-    ix.set_option(_capi.OPT_PATH, path)
+    want = _set_path(ix, path)
     ix.set_option(_capi.OPT_FORCE_EXACT, 0)
+    if path == "scan" and nq > 300:
+        pytest.skip("K-scan serves tiny batches")
     q = oracle.synth_queries(DIMS, nq, n, n_clusters=8)
     st = _check(ix, pk, q, k)
-    assert st["path"] == path
+    assert st["path"] == want
+    _set_path(ix, "auto")
 
 
 def test_search_auto_path_and_fallback_tc(db20k):
     from image_recommender_b200 import _capi
     ix, pk, n = db20k
-    ix.set_option(_capi.OPT_PATH, 0)
-    q = oracle.synth_queries(DIMS, 9, n, n_clusters=8, qseed=99)
+    _set_path(ix, "auto")
+    q = oracle.synth_queries(DIMS, 200, n, n_clusters=8, qseed=99)
     assert _check(ix, pk, q[:1], 10)["path"] == 1
-    assert _check(ix, pk, q, 10)["path"] == 2
+    assert _check(ix, pk, q[:9], 10)["path"] == 2
+    assert _check(ix, pk, q, 10)["path"] == 3
+    q = q[:9]
     # exhaustive fp32 scan (the route of uncertified queries) returns the same bits
     ix.set_option(_capi.OPT_FORCE_EXACT, 1)
     st = _check(ix, pk, q, 10)
@@ -146,12 +160,12 @@ def test_search_tight_candidate_budget_falls_back_tc(db20k):
     ix, pk, n = db20k
     ix.set_option(_capi.OPT_RERANK, 32)
     q = oracle.synth_queries(DIMS, 6, n, n_clusters=8, qseed=7)
-    for path in (1, 2):
-        ix.set_option(_capi.OPT_PATH, path)
+    for path in ("scan", "tc", "tc2"):
+        _set_path(ix, path)
         st = _check(ix, pk, q, 10)
-    assert st["n_uncertified"] > 0
+        assert st["n_uncertified"] > 0
     ix.set_option(_capi.OPT_RERANK, 0)
-    ix.set_option(_capi.OPT_PATH, 0)
+    _set_path(ix, "auto")
 
 
 def test_self_query_rank0(db20k):
@@ -173,9 +187,8 @@ def test_k_larger_than_ntotal_pads_minus_one_tc(gpu):
     ix = irb.FlatShard(DIMS, 3, device=gpu)
     ix.add_tables(tabs)
     q = oracle.synth_queries(DIMS, 2, 3, n_clusters=8)
-    for path in (1, 2):
-        from image_recommender_b200 import _capi
-        ix.set_option(_capi.OPT_PATH, path)
+    for path in ("scan", "tc", "tc2"):
+        _set_path(ix, path)
         dist, lab, ip = ix.search_ip(q, 5)
         assert (lab[:, 3:] == -1).all() and (lab[:, :3] >= 0).all()
         _check(ix, pk, q, 5)
@@ -202,8 +215,8 @@ def test_duplicate_rows_tie_break_by_offset_tc(gpu):
     ix = irb.FlatShard(DIMS, 600, device=gpu)
     ix.add_tables(tabs)
     q = oracle.normalize_l2(pk["f32"][[7, 120]])
-    for path in (1, 2):
-        ix.set_option(_capi.OPT_PATH, path)
+    for path in ("scan", "tc", "tc2"):
+        _set_path(ix, path)
         _check(ix, pk, q, 32)
     ix.close()
 
@@ -277,8 +290,8 @@ def test_large_scale_properties_tc(gpu):
     q = ix.synth_queries_device(nq, total_rows=n)
     src = np.array([oracle.synth_query_source(0x5EED, i, n) for i in range(nq)])
     res = {}
-    for path, m in ((1, 8), (2, nq)):
-        ix.set_option(_capi.OPT_PATH, path)
+    for path, m in (("scan", 8), ("tc", nq), ("tc2", nq)):
+        _set_path(ix, path)
         dist, lab, ip = ix.search_device(q[:m].contiguous(), k)
         torch.cuda.synchronize()
         lab = lab.cpu().numpy(); dist = dist.cpu().numpy()
@@ -286,6 +299,8 @@ def test_large_scale_properties_tc(gpu):
         assert (np.diff(dist, axis=1) >= 0).all()
         assert ix.stats()["n_uncertified"] <= m // 10
         res[path] = (lab, ip.cpu().numpy())
-    assert np.array_equal(res[1][0], res[2][0][:8])
-    assert np.array_equal(res[1][1].view(np.uint32), res[2][1][:8].view(np.uint32))
+    for other in ("tc", "tc2"):
+        assert np.array_equal(res["scan"][0], res[other][0][:8])
+        assert np.array_equal(res["scan"][1].view(np.uint32), res[other][1][:8].view(np.uint32))
+    assert np.array_equal(res["tc"][0], res["tc2"][0])
     ix.close()
