@@ -287,7 +287,7 @@ def main():
     tc_ach = flops / (score_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": tc_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": tc_ach / peaks["bf16_tflops"], "traffic": None,
-                "kernel": "score_tc_kernel" if st["path"] == 2 else "scan_bf16_kernel",
+                "kernel": {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st["path"]],
                 "kernel_ms": score_ms, "peak_source": peaks["source"] + " burst (kernel timed alone per step)",
                 "algorithmic_flops_per_launch": flops}
 
@@ -299,7 +299,8 @@ def main():
     hbm_ach = bytes_b1 / (s1_ms * 1e-3) / 1e9
     roofline_b1 = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None,
-                   "kernel": "scan_bf16_kernel" if st1["path"] == 1 else "score_tc_kernel", "kernel_ms": s1_ms,
+                   "kernel": {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st1["path"]],
+                   "kernel_ms": s1_ms,
                    "qps": 1e3 / ms_b1, "ms_per_query": ms_b1, "tail_ms": t1_ms,
                    "algorithmic_bytes_per_launch": bytes_b1}
 

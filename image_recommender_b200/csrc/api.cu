@@ -53,7 +53,7 @@ struct Workspace {
   int nq_cap = 0, n_lists = 0, cand_cap = 0, exact_splits = 0;
   float* q = nullptr;             // [nq, D] staging for the host API
   uint16_t* q_bf16 = nullptr;     // [nq_pad, Dp]
-  float *qn2 = nullptr, *eps_scan = nullptr, *eps_tc = nullptr, *thr = nullptr;
+  float *qn2 = nullptr, *eps_scan = nullptr, *eps_tc = nullptr, *thr = nullptr, *thr_floor = nullptr;
   Cand* partial = nullptr;        // [nq, n_lists, 32]
   int32_t *cand_rows = nullptr, *cand_count = nullptr, *flags = nullptr;
   float* cand_ip = nullptr;
@@ -62,7 +62,7 @@ struct Workspace {
   float *out_ip = nullptr, *out_dist = nullptr;
   int64_t* out_labels = nullptr;
   void release() {
-    dev_free(q); dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr);
+    dev_free(q); dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr); dev_free(thr_floor);
     dev_free(partial); dev_free(cand_rows); dev_free(cand_count); dev_free(flags); dev_free(cand_ip);
     dev_free(fail_count); dev_free(fail_list); dev_free(exact_partial);
     dev_free(out_ip); dev_free(out_dist); dev_free(out_labels);
@@ -94,6 +94,7 @@ struct b2k_index {
   const void* tmap_q_ptr = nullptr; int tmap_q_rows = 0;
   const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
   int opt_pair = -1;                          // -1 auto (nq > 128), 0 never, 1 always
+  int opt_seed = 1;                           // threshold seeding for the tcgen05 paths
   // options
   int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 1, opt_splits = 0;
   b2k_stats stats;
@@ -147,6 +148,7 @@ int ensure_workspace(b2k_index* ix, int nq) {
   if ((rc = dev_alloc(&w.eps_scan, cap))) return rc;
   if ((rc = dev_alloc(&w.eps_tc, cap))) return rc;
   if ((rc = dev_alloc(&w.thr, cap))) return rc;
+  if ((rc = dev_alloc(&w.thr_floor, cap))) return rc;
   if ((rc = dev_alloc(&w.partial, (size_t)cap * n_lists * kList))) return rc;
   if ((rc = dev_alloc(&w.cand_rows, (size_t)cap * cand_cap))) return rc;
   if ((rc = dev_alloc(&w.cand_ip, (size_t)cap * cand_cap))) return rc;
@@ -218,7 +220,25 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     ta.tmap_q = &ix->tmap_q; ta.tmap_db = pair ? &ix->tmap_db2 : &ix->tmap_db;
     ta.n_rows = ix->ntotal; ta.Dp = ix->Dp; ta.nq = nq;
     ta.plan = pair ? score_tc2_plan(nq, ix->ntotal, ix->n_sm, forced) : score_tc_plan(nq, ix->ntotal, ix->n_sm, forced);
-    ta.partial = w.partial; ta.n_lists = w.n_lists;
+    ta.partial = w.partial; ta.n_lists = w.n_lists; ta.max_tiles = 0; ta.thr_floor = nullptr;
+    // Threshold seeding: a sampling pass over the first tiles of every split bounds each query's
+    // k-th best score from below, so the full pass admits only rows that can still matter and
+    // the fused selection stops being the epilogue's bottleneck (DESIGN.md "seeding").
+    const int64_t tiles_total = (ix->ntotal + 255) / 256;
+    const int sample_tiles = 2;
+    const bool seed = ix->opt_seed && tiles_total >= (int64_t)16 * ta.plan.n_splits;
+    if (seed) {
+      ta.max_tiles = sample_tiles;
+      rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
+      if (rc) return rc;
+      SeedArgs sd;
+      sd.partial = w.partial; sd.n_lists = ta.plan.n_splits; sd.list_stride = w.n_lists; sd.k = k;
+      sd.eps = w.eps_tc; sd.thr_floor = w.thr_floor;
+      rc = launch_seed(sd, nq, st);
+      if (rc) return rc;
+      launches += 2;
+      ta.max_tiles = 0; ta.thr_floor = w.thr_floor;
+    }
     rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
     if (rc) return rc;
     ++launches;
@@ -551,6 +571,8 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
     case B2K_OPT_SPLITS:
       if (value < 0 || value > 4096) break;
       ix->opt_splits = (int)value; return 0;
+    case B2K_OPT_SEED:
+      ix->opt_seed = value != 0; return 0;
     case B2K_OPT_TC_PAIR:
       if (value < -1 || value > 1) break;
       ix->opt_pair = (int)value; return 0;

@@ -149,7 +149,17 @@ struct ScoreTcArgs {
   ScoreTcPlan plan;
   Cand* partial;        // [nq, n_lists, kList]; CTA (qtile, split) fills list `split`
   int32_t n_lists;
+  int32_t max_tiles;    // > 0: sampling pass, every split scores only its first max_tiles tiles
+  const float* thr_floor;   // [nq] seeded admission floor (may be null)
 };
+
+// Threshold seeding: from the partial lists of a sampling pass, floor[q] = (k-th best sampled
+// score) - 2 eps[q], one ulp lower.  No row of the shard below it can be a re-rank candidate.
+struct SeedArgs {
+  const Cand* partial; int32_t n_lists, list_stride, k;
+  const float* eps; float* thr_floor;
+};
+int launch_seed(const SeedArgs& a, int nq, cudaStream_t st);
 bool score_tc_supports(int Dp);
 ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits);
 int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_bf16, int nq_pad,

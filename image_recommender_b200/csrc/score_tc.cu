@@ -31,7 +31,7 @@ constexpr uint32_t kIdesc = make_idesc(kBlockM, kBlockN);
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                 int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
-                int32_t n_lists, Cand* __restrict__ partial) {
+                int32_t n_lists, int32_t max_tiles, const float* __restrict__ thr_floor, Cand* __restrict__ partial) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -50,7 +50,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
   const int64_t tile_begin = tiles_total * split / n_splits;
   const int64_t tile_end = tiles_total * (split + 1) / n_splits;
-  const int n_tiles = (int)(tile_end - tile_begin);
+  int n_tiles = (int)(tile_end - tile_begin);
+  if (max_tiles > 0 && n_tiles > max_tiles) n_tiles = max_tiles;   // sampling pass (threshold seeding)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
@@ -114,11 +115,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
     const int m = quarter * 32 + lane;               // query row inside the tile
     const int qi = qtile * kBlockM + m;
-    float* my_s = lscore + m;                        // entry e at my_s[e * 128]
-    int32_t* my_r = lrow + m;
-#pragma unroll
-    for (int e = 0; e < kList; ++e) { my_s[e * kBlockM] = -INFINITY; my_r[e * kBlockM] = -1; }
-    float thr = -INFINITY;
+    const uint32_t s_addr = ptx::smem_u32(lscore + m);            // entry e at + e * 512 B
+    const uint32_t r_addr = ptx::smem_u32(lrow + m);
+    list_init(s_addr, r_addr);
+    // padded query rows (qi >= nq) never insert; seeded floor = b_k(sample) - 2 eps (api.cu)
+    const float floor = qi < nq ? (thr_floor ? thr_floor[qi] : -INFINITY) : INFINITY;
+    float thr = floor;
     int min_e = 0;
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
@@ -127,18 +129,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
-      drain_accumulator(taddr, row0, valid, my_s, my_r, thr, min_e);
+      drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
     }
     if (qi < nq) {
-      Cand* out = partial + ((int64_t)qi * n_lists + split) * kList;
-#pragma unroll 4
-      for (int e = 0; e < kList; ++e) {
-        Cand c; c.score = my_s[e * kBlockM]; c.row = my_r[e * kBlockM];
-        out[e] = c;
-      }
+      list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
     }
   }
 
@@ -213,7 +210,7 @@ int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st) {
   const CUtensorMap* mq = reinterpret_cast<const CUtensorMap*>(a.tmap_q);
   const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(a.tmap_db);
   score_tc_kernel<<<a.plan.grid, kThreads, kSmemBytes, st>>>(*mq, *md, a.n_rows, a.Dp / kBlockK, a.nq,
-                                                            a.plan.n_qtiles, a.plan.n_splits, a.n_lists,
+                                                            a.plan.n_qtiles, a.plan.n_splits, a.n_lists, a.max_tiles, a.thr_floor,
                                                             a.partial);
   B2K_CHECK_LAUNCH();
   return 0;

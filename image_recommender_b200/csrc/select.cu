@@ -47,6 +47,42 @@ __device__ __forceinline__ uint64_t block_max_u64(uint64_t v, uint64_t* scratch)
   return scratch[32];
 }
 
+// k-th best score key over skey[0..E) (0 = fewer than k real entries), block-cooperative.
+__device__ __forceinline__ uint32_t block_kth_key(const uint32_t* skey, int E, int k, uint64_t* scratch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t prev = 0xffffffffu;   // exclusive upper bound (no finite float has this key)
+  int covered = 0;
+  for (int it = 0; it < k; ++it) {
+    uint32_t m = 0u;
+    for (int e = tid; e < E; e += kSelThreads) {
+      const uint32_t v = skey[e];
+      if (v < prev && v > m) m = v;
+    }
+    const uint32_t gmax = (uint32_t)block_max_u64((uint64_t)m, scratch);
+    if (gmax == 0u) return 0u;                     // fewer than k real entries
+    int c = 0;
+    for (int e = tid; e < E; e += kSelThreads) c += (skey[e] == gmax);
+    uint64_t tot = (uint64_t)c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = tot;
+    __syncthreads();
+    uint64_t all = 0;
+    for (int w = 0; w < (kSelThreads >> 5); ++w) all += scratch[w];
+    covered += (int)all;
+    prev = gmax;
+    if (covered >= k) return gmax;
+  }
+  return 0u;
+}
+
+// score of key - 2*eps, rounded down (conservative)
+__device__ __forceinline__ float key_minus_2eps(uint32_t key, float eps) {
+  const uint32_t b = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  return __fsub_rd(__uint_as_float(b), __fmul_ru(2.0f, eps));
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -68,41 +104,10 @@ select_kernel(SelectArgs a) {
   }
   __syncthreads();
 
-  // b_k: walk distinct score keys downward until k entries are covered.
-  // packs (key << 32 | multiplicity-capped count) so one block reduction does both.
-  uint32_t prev = 0xffffffffu;   // exclusive upper bound (no finite float has this key)
-  int covered = 0;
-  uint32_t bk = 0u;
-  for (int it = 0; it < a.k; ++it) {
-    uint32_t m = 0u;
-    for (int e = tid; e < E; e += kSelThreads) {
-      const uint32_t v = skey[e];
-      if (v < prev && v > m) m = v;
-    }
-    const uint32_t gmax = (uint32_t)block_max_u64((uint64_t)m, scratch);
-    if (gmax == 0u) { bk = 0u; break; }            // fewer than k real entries
-    int c = 0;
-    for (int e = tid; e < E; e += kSelThreads) c += (skey[e] == gmax);
-    // count via block reduction on the same scratch (sum fits: E < 2^31)
-    uint64_t tot = (uint64_t)c;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    __syncthreads();
-    if (lane == 0) scratch[warp] = tot;
-    __syncthreads();
-    uint64_t all = 0;
-    for (int w = 0; w < (kSelThreads >> 5); ++w) all += scratch[w];
-    covered += (int)all;
-    bk = gmax; prev = gmax;
-    if (covered >= a.k) break;
-  }
-  // threshold (in score space).  bk == 0: fewer than k rows listed -> everything is a candidate.
-  float thr = -INFINITY;
-  if (bk != 0u && covered >= a.k) {
-    const uint32_t b = (bk & 0x80000000u) ? (bk & 0x7fffffffu) : ~bk;
-    const float bks = __uint_as_float(b);
-    thr = __fsub_rd(bks, __fmul_ru(2.0f, a.eps[q]));   // round the threshold down: conservative
-  }
+  // b_k = k-th best approximate score over every list; bk == 0: fewer than k rows listed ->
+  // everything listed is a candidate.
+  const uint32_t bk = block_kth_key(skey, E, a.k, scratch);
+  const float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
 
   // candidates + saturation.  Warp w owns lists w, w+8, ...; lane j = entry j of the list.
   int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
@@ -133,6 +138,27 @@ select_kernel(SelectArgs a) {
     a.cand_count[q] = cnt;
     a.flags[q] = flag;
     a.thr[q] = thr;
+  }
+}
+
+// One CTA per query: admission floor for the full pass from the lists of the sampling pass.
+__global__ void __launch_bounds__(kSelThreads)
+seed_kernel(SeedArgs a) {
+  extern __shared__ uint32_t skey[];
+  __shared__ uint64_t scratch[33];
+  const int q = blockIdx.x;
+  const int E = a.n_lists * kList;
+  const Cand* lst = a.partial + (int64_t)q * a.list_stride * kList;
+  for (int e = threadIdx.x; e < E; e += kSelThreads) {
+    const Cand c = lst[e];
+    skey[e] = c.row < 0 ? 0u : float_key(c.score);
+  }
+  __syncthreads();
+  const uint32_t bk = block_kth_key(skey, E, a.k, scratch);
+  if (threadIdx.x == 0) {
+    // strictly below b_k(sample) - 2 eps <= b_k(shard) - 2 eps: rows at or under the floor are
+    // never candidates, and rows above it are admitted (strict compare in the scoring epilogue)
+    a.thr_floor[q] = bk != 0u ? nextafterf(key_minus_2eps(bk, a.eps[q]), -INFINITY) : -INFINITY;
   }
 }
 
@@ -274,6 +300,15 @@ int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   select_kernel<<<nq, kSelThreads, smem, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_seed(const SeedArgs& a, int nq, cudaStream_t st) {
+  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint32_t);
+  if (smem > 48 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  seed_kernel<<<nq, kSelThreads, smem, st>>>(a);
   B2K_CHECK_LAUNCH();
   return 0;
 }

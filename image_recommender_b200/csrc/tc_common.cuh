@@ -31,16 +31,33 @@ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Per-thread top-32 lists live in shared memory as [entry][128 threads] (conflict-free across a
+// warp); they are addressed with 32-bit shared-window addresses so the accesses are LDS/STS.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int32_t lds_s32(uint32_t a) {
+  int32_t v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int32_t v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+constexpr uint32_t kEntryStride = kBlockM * 4;   // bytes between consecutive entries of one thread
+
 // Replace the worst entry (slot min_e) of a per-thread list and rescan for the new worst.
-// Returns (new worst slot << 32) | bits(new worst score); the score is the admission threshold.
-static __device__ __noinline__ uint64_t list_insert(float* my_s, int32_t* my_r, int min_e, float sc, int32_t row) {
-  my_s[min_e * kBlockM] = sc;
-  my_r[min_e * kBlockM] = row;
+// Returns (new worst slot << 32) | bits(new worst score).
+static __device__ __noinline__ uint64_t list_insert(uint32_t s_addr, uint32_t r_addr, int min_e, float sc, int32_t row) {
+  sts_f32(s_addr + (uint32_t)min_e * kEntryStride, sc);
+  sts_s32(r_addr + (uint32_t)min_e * kEntryStride, row);
   float mn = INFINITY;
   int me = 0;
 #pragma unroll
   for (int e = 0; e < kList; ++e) {
-    const float se = my_s[e * kBlockM];
+    const float se = lds_f32(s_addr + (uint32_t)e * kEntryStride);
     if (se < mn) { mn = se; me = e; }
   }
   return ((uint64_t)(uint32_t)me << 32) | (uint64_t)__float_as_uint(mn);
@@ -48,9 +65,10 @@ static __device__ __noinline__ uint64_t list_insert(float* my_s, int32_t* my_r, 
 
 // Drain one 128 x 256 accumulator: this thread owns TMEM lane (= query row) `taddr`'s lane field and
 // filters the 256 scores of DB rows row0 .. row0+255 (only the first `valid` are real rows)
-// against its running threshold.
-__device__ __forceinline__ void drain_accumulator(uint32_t taddr, int64_t row0, int valid, float* my_s,
-                                                  int32_t* my_r, float& thr, int& min_e) {
+// against its admission threshold thr = max(worst listed score if the list is full, floor).
+// `floor` is the seeded per-query bound (a row below it cannot be a re-rank candidate).
+__device__ __forceinline__ void drain_accumulator(uint32_t taddr, int64_t row0, int valid, uint32_t s_addr,
+                                                  uint32_t r_addr, float floor, float& thr, int& min_e) {
 #pragma unroll 1
   for (int c = 0; c < kBlockN / 32; ++c) {
     uint32_t v[32];
@@ -74,12 +92,30 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, int64_t row0, 
       for (int j = 0; j < 32; ++j) {
         const float sc = __uint_as_float(v[j]);
         if (sc > thr) {
-          const uint64_t r = list_insert(my_s, my_r, min_e, sc, (int32_t)(row0 + c * 32 + j));
-          thr = __uint_as_float((uint32_t)r);
+          const uint64_t r = list_insert(s_addr, r_addr, min_e, sc, (int32_t)(row0 + c * 32 + j));
+          thr = fmaxf(__uint_as_float((uint32_t)r), floor);
           min_e = (int)(r >> 32);
         }
       }
     }
+  }
+}
+
+// Epilogue prologue / epilogue shared by both kernels.
+__device__ __forceinline__ void list_init(uint32_t s_addr, uint32_t r_addr) {
+#pragma unroll
+  for (int e = 0; e < kList; ++e) {
+    sts_f32(s_addr + (uint32_t)e * kEntryStride, -INFINITY);
+    sts_s32(r_addr + (uint32_t)e * kEntryStride, -1);
+  }
+}
+__device__ __forceinline__ void list_store(uint32_t s_addr, uint32_t r_addr, Cand* out) {
+#pragma unroll 4
+  for (int e = 0; e < kList; ++e) {
+    Cand c;
+    c.score = lds_f32(s_addr + (uint32_t)e * kEntryStride);
+    c.row = lds_s32(r_addr + (uint32_t)e * kEntryStride);
+    out[e] = c;
   }
 }
 

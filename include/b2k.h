@@ -43,6 +43,7 @@ typedef struct b2k_index b2k_index;
 #define B2K_OPT_FORCE_EXACT   3  /* 1 = treat every query as uncertified (exercise the exact fp32 scan) */
 #define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 1)    */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
+#define B2K_OPT_SEED          7  /* K-score threshold seeding from a sampling pass: 1 on (default), 0 off */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs when nq > 128), 0 single CTA, 1 pairs */
 
 typedef struct b2k_stats {

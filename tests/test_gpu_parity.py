@@ -138,6 +138,25 @@ def test_search_matches_oracle(db20k, path, nq, k):
     _set_path(ix, "auto")
 
 
+@pytest.mark.parametrize("path", ["tc", "tc2"])
+def test_seeded_threshold_matches_oracle_tc(db20k, path):
+    """With 4 DB splits every split has ~20 tiles, so the sampling pass + seeded admission floor
+    (DESIGN.md "seeding") is active; results must not change by a bit, with or without it."""
+    from image_recommender_b200 import _capi
+    ix, pk, n = db20k
+    _set_path(ix, path)
+    ix.set_option(_capi.OPT_SPLITS, 4)
+    for nq, k in ((5, 10), (300, 10), (64, 32)):
+        q = oracle.synth_queries(DIMS, nq, n, n_clusters=8, qseed=1000 + nq)
+        for seed in (1, 0):
+            ix.set_option(_capi.OPT_SEED, seed)
+            st = _check(ix, pk, q, k)
+            assert st["launches"] == (9 if seed else 7)
+    ix.set_option(_capi.OPT_SEED, 1)
+    ix.set_option(_capi.OPT_SPLITS, 0)
+    _set_path(ix, "auto")
+
+
 def test_search_auto_path_and_fallback_tc(db20k):
     from image_recommender_b200 import _capi
     ix, pk, n = db20k
