@@ -323,3 +323,28 @@ def test_large_scale_properties_tc(gpu):
         assert np.array_equal(res["scan"][1].view(np.uint32), res[other][1][:8].view(np.uint32))
     assert np.array_equal(res["tc"][0], res["tc2"][0])
     ix.close()
+
+
+def test_faiss_shim_protocol(gpu, tmp_path):
+    """The members of the faiss namespace the reference touches, served by the engine
+    (INTEGRATION.md §2): construction, hnsw params, is_trained/train, add, ntotal, search,
+    write_index/read_index, normalize_L2."""
+    import image_recommender_b200.faiss_shim as faiss
+    tabs, pk = _mk(700)
+    arr = np.concatenate(tabs, axis=1)
+    index = faiss.IndexIVFPQ(faiss.IndexHNSWFlat(1968, 32), 1968, 2048, 48, 12)
+    index.table_dims = DIMS
+    index.hnsw.efConstruction = 200
+    assert index.is_trained and index.ntotal == 0
+    index.train(arr)
+    index.add(arr[:300]); index.add(arr[300:])
+    assert index.ntotal == 700
+    q = oracle.synth_queries(DIMS, 1, 700, n_clusters=8)
+    qq = q.copy(); faiss.normalize_L2(qq)
+    d, i = index.search(qq, 5)
+    wd, wi, _ = oracle.search_exact(pk["f32"], oracle.normalize_l2(q), 5, pk["norm2"])
+    assert np.array_equal(i, wi) and np.array_equal(d.view(np.uint32), wd.view(np.uint32))
+    faiss.write_index(index, str(tmp_path / "x.faiss"))
+    back = faiss.read_index(str(tmp_path / "x.faiss"))
+    d2, i2 = back.search(qq, 5)
+    assert back.ntotal == 700 and np.array_equal(i2, wi) and np.array_equal(d2.view(np.uint32), wd.view(np.uint32))
