@@ -304,6 +304,30 @@ def main():
                    "qps": 1e3 / ms_b1, "ms_per_query": ms_b1, "tail_ms": t1_ms,
                    "algorithmic_bytes_per_launch": bytes_b1}
 
+    # ---- K-pack (build half) timed alone on device-resident per-table rows
+    pack = None
+    if rank == 0:
+        n_pack, reps = 131072, 6
+        scratch = irb.FlatShard(DIMS, n_pack * (reps + 2), device=local_rank)
+        tabs = [torch.randn((n_pack, d), device=dev, dtype=torch.float32) for d in DIMS]
+        for _ in range(2):
+            scratch.add_tables_device(tabs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            scratch.add_tables_device(tabs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_pack = e0.elapsed_time(e1) / reps
+        bytes_pack = n_pack * (4.0 * D + 4.0 * D + 2.0 * 1984 + 4.0)     # read fp32, write fp32 + bf16 + norm
+        pack = {"bound": "hbm", "kernel": "pack_rows_kernel", "rows_per_launch": n_pack, "kernel_ms": ms_pack,
+                "achieved": bytes_pack / (ms_pack * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": bytes_pack / (ms_pack * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "rows_per_s": n_pack / (ms_pack * 1e-3)}
+        scratch.close()
+        del tabs
+
     sweep = {}
     for b in [int(x) for x in args.sweep.split(",") if x]:
         qb = shard.synth_queries_device(b, total_rows=n_total, qseed=0x5EED + b)
@@ -339,7 +363,7 @@ def main():
             "extra": {"score_ms": score_ms, "tail_ms": tail_ms, "uncertified_queries": n_unc,
                       "launches_per_step": launches, "build_rows_per_s": n_local / build_s,
                       "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * 1984) / build_s / 1e9,
-                      "host_cores": len(os.sched_getaffinity(0)), "sweep": sweep},
+                      "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -48,6 +48,7 @@ SIGNATURES = {
     "b2k_destroy": (None, [C.c_void_p]),
     "b2k_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
     "b2k_capacity": (C.c_int64, [C.c_void_p]),
+    "b2k_reset": (C.c_int, [C.c_void_p]),
     "b2k_add": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64]),
     "b2k_add_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64, C.c_void_p]),
     "b2k_ntotal": (C.c_int64, [C.c_void_p]),

@@ -25,7 +25,7 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
-constexpr int64_t kStageRows = 16384;     // rows per host->device staging chunk of add()/load()
+constexpr int64_t kStageRows = 65536;     // rows per staging chunk of add() / load() / fill_synthetic()
 constexpr int kMaxNqPerPass = 16384;      // queries per pipeline pass (workspace sizing)
 constexpr int kDefaultCandCap = 0;      // 0: every listed entry can be a candidate (no overflow)
 
@@ -225,8 +225,8 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // k-th best score from below, so the full pass admits only rows that can still matter and
     // the fused selection stops being the epilogue's bottleneck (DESIGN.md "seeding").
     const int64_t tiles_total = (ix->ntotal + 255) / 256;
-    const int sample_tiles = 2;
     const bool seed = ix->opt_seed && tiles_total >= (int64_t)16 * ta.plan.n_splits;
+    const int sample_tiles = tiles_total >= (int64_t)96 * ta.plan.n_splits ? 2 : 1;   // <= ~3 % extra work
     if (seed) {
       ta.max_tiles = sample_tiles;
       rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
@@ -403,6 +403,16 @@ void b2k_destroy(b2k_index* ix) {
 }
 
 int64_t b2k_capacity(const b2k_index* ix) { return ix ? ix->cap : 0; }
+
+int b2k_reset(b2k_index* ix) {
+  if (!ix) { set_error("reset: null index"); return B2K_E_INVALID; }
+  DeviceGuard g(ix->device);
+  B2K_CUDA(cudaDeviceSynchronize());
+  B2K_CUDA(cudaMemset(ix->stat_bits, 0, 2 * sizeof(unsigned int)));
+  ix->ntotal = 0;
+  ix->tmap_db_ptr = nullptr;
+  return 0;
+}
 
 int b2k_reserve(b2k_index* ix, int64_t capacity_rows) {
   if (!ix || capacity_rows < ix->ntotal || capacity_rows > 0x7fffff00ll) { set_error("reserve: bad capacity"); return B2K_E_INVALID; }

@@ -36,6 +36,7 @@ pack_rows_kernel(PackArgs a) {
                      ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (vec) {
       const float4* x4 = reinterpret_cast<const float4*>(x);
+      // the second read of x hits L1 (the warp just streamed the row for the norm)
       for (int c = lane; c < (d >> 2); c += 32) {
         float4 v = x4[c];
         v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv);
@@ -48,12 +49,12 @@ pack_rows_kernel(PackArgs a) {
         float d2 = __fsub_rn(bf16_bits_to_f32(b2), v.z), d3 = __fsub_rn(bf16_bits_to_f32(b3), v.w);
         pe = __fmaf_rn(d0, d0, pe); pe = __fmaf_rn(d1, d1, pe);
         pe = __fmaf_rn(d2, d2, pe); pe = __fmaf_rn(d3, d3, pe);
-        if (of) *reinterpret_cast<float4*>(of + off + 4 * c) = v;
-        if (ob) {
+        if (of) __stcs(reinterpret_cast<float4*>(of + off + 4 * c), v);      // streaming stores: the
+        if (ob) {                                                             // packed rows are not re-read
           uint2 pk;
           pk.x = (uint32_t)b0 | ((uint32_t)b1 << 16);
           pk.y = (uint32_t)b2 | ((uint32_t)b3 << 16);
-          *reinterpret_cast<uint2*>(ob + off + 4 * c) = pk;
+          __stcs(reinterpret_cast<uint2*>(ob + off + 4 * c), pk);
         }
       }
     } else {
@@ -79,9 +80,12 @@ pack_rows_kernel(PackArgs a) {
     if (a.out_norm2) a.out_norm2[r_out] = n2;
     // non-negative floats order like their bit patterns; NaN (bad input rows) poisons the
     // bound on purpose: its pattern is above +inf, so certificates fail -> exact scan.
+    // The maxima only grow: skip the atomic unless this row raises them (one hot L2 address
+    // shared by every warp would otherwise serialise the whole kernel's tail).
     if (a.stat_bits) {
-      atomicMax(a.stat_bits + 0, __float_as_uint(e2));
-      atomicMax(a.stat_bits + 1, __float_as_uint(n2));
+      const unsigned int eb = __float_as_uint(e2), nb = __float_as_uint(n2);
+      if (eb > __ldcg(a.stat_bits + 0)) atomicMax(a.stat_bits + 0, eb);
+      if (nb > __ldcg(a.stat_bits + 1)) atomicMax(a.stat_bits + 1, nb);
     }
   }
 }

@@ -93,6 +93,10 @@ class FlatShard:
     def train(self, x=None) -> None:   # create_index.py:298 — nothing to train for exact search
         return None
 
+    def reset(self) -> None:
+        """index.reset(): drop every row, keep the allocation."""
+        check(_lib.b2k_reset(self._h))
+
     def reserve(self, capacity: int) -> None:
         check(_lib.b2k_reserve(self._h, int(capacity)))
 

@@ -82,6 +82,8 @@ void b2k_destroy(b2k_index* idx);
  * capacity_rows >= ntotal and moves the rows device-to-device (bits unchanged). */
 int b2k_reserve(b2k_index* idx, int64_t capacity_rows);
 int64_t b2k_capacity(const b2k_index* idx);
+/* index.reset(): forget every row (capacity and allocations are kept). */
+int b2k_reset(b2k_index* idx);
 
 /* Replaces index.add(arr) (main/create_index.py:311) fused with the per-row
  * np.concatenate of _process_batch (main/create_index.py:176-188): host_tables[t] is a
