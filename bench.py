@@ -47,6 +47,18 @@ def parse_args():
     return ap.parse_args()
 
 
+def load_traffic(kernel: str, rows_local: int, batch: int):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on exactly
+    this workload (profiles/r01_traffic.json); else None."""
+    p = ROOT / "profiles" / "r01_traffic.json"
+    if not p.exists():
+        return None
+    t = json.loads(p.read_text()).get(kernel)
+    if t and t["rows_local"] == rows_local and t["batch"] == batch:
+        return t["dram_bytes"]
+    return None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -285,9 +297,10 @@ def main():
 
     flops = 2.0 * B * n_local * D
     tc_ach = flops / (score_ms * 1e-3) / 1e12
+    kname = {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st["path"]]
     roofline = {"bound": "tensor", "achieved": tc_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": tc_ach / peaks["bf16_tflops"], "traffic": None,
-                "kernel": {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st["path"]],
+                "frac": tc_ach / peaks["bf16_tflops"], "traffic": load_traffic(kname, n_local, B),
+                "kernel": kname,
                 "kernel_ms": score_ms, "peak_source": peaks["source"] + " burst (kernel timed alone per step)",
                 "algorithmic_flops_per_launch": flops}
 
@@ -297,9 +310,10 @@ def main():
     s1_ms, t1_ms, l1, _, st1 = kernel_times(q1, 10)
     bytes_b1 = 2.0 * n_local * D
     hbm_ach = bytes_b1 / (s1_ms * 1e-3) / 1e9
+    kname1 = {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st1["path"]]
     roofline_b1 = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None,
-                   "kernel": {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st1["path"]],
+                   "frac": hbm_ach / peaks["hbm_gbs"], "traffic": load_traffic(kname1, n_local, 1),
+                   "kernel": kname1,
                    "kernel_ms": s1_ms,
                    "qps": 1e3 / ms_b1, "ms_per_query": ms_b1, "tail_ms": t1_ms,
                    "algorithmic_bytes_per_launch": bytes_b1}

@@ -172,20 +172,20 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   int launches = 0;
   const int nq_pad = (nq + 255) / 256 * 256;
 
-  QueryPrepArgs qp;
-  qp.q = q_dev; qp.q_bf16 = w.q_bf16; qp.qn2 = w.qn2; qp.eps_scan = w.eps_scan; qp.eps_tc = w.eps_tc;
-  qp.stat_bits = ix->stat_bits;
-  qp.nq = nq; qp.nq_pad = nq_pad; qp.D = ix->D; qp.Dp = ix->Dp;
-  int rc = launch_query_prep(qp, st);
-  if (rc) return rc;
-  ++launches;
-  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, sizeof(int32_t), st));
-
   // ---- path selection
   int path = ix->opt_path;
   if (path == 0) path = (nq <= ix->opt_scan_max_b && scan_supports(ix->Dp)) ? 1 : 2;
   if (path == 2 && (!score_tc_supports(ix->Dp) || ix->ntotal == 0)) path = 1;
   if (path == 1 && !scan_supports(ix->Dp)) { set_error("no scoring path supports Dp=%d", ix->Dp); return B2K_E_INVALID; }
+
+  QueryPrepArgs qp;
+  qp.q = q_dev; qp.q_bf16 = path == 1 ? nullptr : w.q_bf16; qp.qn2 = w.qn2; qp.eps_scan = w.eps_scan;
+  qp.eps_tc = w.eps_tc; qp.stat_bits = ix->stat_bits;
+  qp.nq = nq; qp.nq_pad = path == 1 ? nq : nq_pad; qp.D = ix->D; qp.Dp = ix->Dp;
+  int rc = launch_query_prep(qp, st);
+  if (rc) return rc;
+  ++launches;
+  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, sizeof(int32_t), st));
 
   int n_lists_used = 0;
   const float* eps = nullptr;

@@ -116,9 +116,13 @@ query_prep_kernel(QueryPrepArgs a) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= a.nq_pad) return;
-  uint16_t* ob = a.q_bf16 + (int64_t)w * a.Dp;
+  // q_bf16 == nullptr: the K-scan path multiplies the fp32 query directly (nothing to pack)
+  uint16_t* ob = a.q_bf16 ? a.q_bf16 + (int64_t)w * a.Dp : nullptr;
   if (w >= a.nq) {
-    for (int i = lane; i < a.Dp; i += 32) ob[i] = 0;
+    if (ob) {   // zero rows pad the query tile (Dp is a multiple of 64: 16-byte stores)
+      uint4* o4 = reinterpret_cast<uint4*>(ob);
+      for (int i = lane; i < (a.Dp >> 3); i += 32) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     return;
   }
   const float* q = a.q + (int64_t)w * a.D;
@@ -134,7 +138,7 @@ query_prep_kernel(QueryPrepArgs a) {
       const float df = __fsub_rn(vb, v);
       pd = __fmaf_rn(df, df, pd);
     }
-    ob[i] = b;
+    if (ob) ob[i] = b;
   }
   const float qb2 = warp_sum_f32(pb), qd2 = warp_sum_f32(pd);
   if (lane == 0) {

@@ -31,50 +31,48 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
   return v;
 }
 
-// Block-wide max of a u64 (all threads get the result).  `scratch` has >= 33 slots.
-__device__ __forceinline__ uint64_t block_max_u64(uint64_t v, uint64_t* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = warp_max_u64(v);
-  __syncthreads();                       // scratch reuse across calls
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    uint64_t w = lane < (blockDim.x >> 5) ? scratch[lane] : 0ull;
-    w = warp_max_u64(w);
-    if (lane == 0) scratch[32] = w;
-  }
-  __syncthreads();
-  return scratch[32];
-}
-
-// k-th best score key over skey[0..E) (0 = fewer than k real entries), block-cooperative.
-__device__ __forceinline__ uint32_t block_kth_key(const uint32_t* skey, int E, int k, uint64_t* scratch) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t prev = 0xffffffffu;   // exclusive upper bound (no finite float has this key)
-  int covered = 0;
-  for (int it = 0; it < k; ++it) {
-    uint32_t m = 0u;
-    for (int e = tid; e < E; e += kSelThreads) {
-      const uint32_t v = skey[e];
+// Block-cooperative top-k of n distinct non-zero u64 keys in shared memory (0 = empty slot):
+// every warp extracts the k best of its interleaved share with warp shuffles only (no block
+// barrier inside the loop), then warp 0 merges the nw*k survivors.  out[0..k) = the k largest keys,
+// descending, zero padded.  wtop: nw*32 slots of scratch.  All threads of the block must call.
+__device__ __forceinline__ void block_topk_u64(const uint64_t* keys, int n, int k, uint64_t* wtop, uint64_t* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint64_t prev = ~0ull;
+  for (int j = 0; j < k; ++j) {
+    uint64_t m = 0ull;
+    for (int e = warp * 32 + lane; e < n; e += nw * 32) {
+      const uint64_t v = keys[e];
       if (v < prev && v > m) m = v;
     }
-    const uint32_t gmax = (uint32_t)block_max_u64((uint64_t)m, scratch);
-    if (gmax == 0u) return 0u;                     // fewer than k real entries
-    int c = 0;
-    for (int e = tid; e < E; e += kSelThreads) c += (skey[e] == gmax);
-    uint64_t tot = (uint64_t)c;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    __syncthreads();
-    if (lane == 0) scratch[warp] = tot;
-    __syncthreads();
-    uint64_t all = 0;
-    for (int w = 0; w < (kSelThreads >> 5); ++w) all += scratch[w];
-    covered += (int)all;
-    prev = gmax;
-    if (covered >= k) return gmax;
+    m = warp_max_u64(m);
+    if (lane == 0) wtop[warp * 32 + j] = m;
+    prev = m;
   }
-  return 0u;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t prev2 = ~0ull;
+    for (int j = 0; j < k; ++j) {
+      uint64_t m = 0ull;
+      for (int e = lane; e < nw * k; e += 32) {
+        const uint64_t v = wtop[(e / k) * 32 + (e % k)];
+        if (v < prev2 && v > m) m = v;
+      }
+      m = warp_max_u64(m);
+      if (lane == 0) out[j] = m;
+      prev2 = m;
+    }
+  }
+  __syncthreads();
+}
+
+// Partial-list entries as distinct u64 keys: (order-preserving score key << 32) | reversed slot.
+__device__ __forceinline__ void load_list_keys(const Cand* lst, int E, uint64_t* keys) {
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const Cand c = lst[e];
+    const uint32_t fk = c.row < 0 ? 0u : float_key(c.score);     // NaN scores -> 0: dropped
+    keys[e] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - e)) : 0ull;
+  }
+  __syncthreads();
 }
 
 // score of key - 2*eps, rounded down (conservative)
@@ -86,45 +84,44 @@ __device__ __forceinline__ float key_minus_2eps(uint32_t key, float eps) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// One CTA per query.  Dynamic smem: n_lists*32 u32 score keys.
+// One CTA per query.  Dynamic smem: n_lists*32 u64 keys.
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(SelectArgs a) {
-  extern __shared__ uint32_t skey[];
-  __shared__ uint64_t scratch[33];
+  extern __shared__ uint64_t skey[];
+  __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
+  __shared__ uint64_t top[B2K_MAX_K];
   __shared__ int s_count, s_sat;
   const int q = blockIdx.x;
   const int E = a.n_lists * kList;
   const Cand* lst = a.partial + (int64_t)q * a.list_stride * kList;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { s_count = 0; s_sat = 0; }
+  load_list_keys(lst, E, skey);
 
-  for (int e = tid; e < E; e += kSelThreads) {
-    const Cand c = lst[e];
-    skey[e] = c.row < 0 ? 0u : float_key(c.score);   // real scores have key >= 1 (NaN -> 0: dropped)
-  }
-  __syncthreads();
-
-  // b_k = k-th best approximate score over every list; bk == 0: fewer than k rows listed ->
-  // everything listed is a candidate.
-  const uint32_t bk = block_kth_key(skey, E, a.k, scratch);
+  // b_k = k-th best approximate score over every list; 0: fewer than k rows listed -> everything
+  // listed is a candidate.
+  block_topk_u64(skey, E, a.k, wtop, top);
+  const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
   const float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
 
-  // candidates + saturation.  Warp w owns lists w, w+8, ...; lane j = entry j of the list.
+  // candidates + saturation, from the shared-memory keys (rows are fetched for hits only).
+  // Warp w owns lists w, w+8, ...; lane j = entry j of the list.
+  const uint32_t thr_key = float_key(thr);              // score >= thr  <=>  key >= thr_key
   int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
   for (int l = warp; l < a.n_lists; l += (kSelThreads >> 5)) {
-    const Cand c = lst[l * kList + lane];
-    const bool real = c.row >= 0 && skey[l * kList + lane] != 0u;
-    const bool hit = real && (c.score >= thr);
+    const uint64_t key = skey[l * kList + lane];
+    const uint32_t sk = (uint32_t)(key >> 32);
+    const bool hit = sk != 0u && sk >= thr_key;
     const unsigned hm = __ballot_sync(0xffffffffu, hit);
-    const unsigned rm = __ballot_sync(0xffffffffu, c.row >= 0);
-    if (hm == 0xffffffffu && rm == 0xffffffffu && lane == 0) s_sat = 1;   // list full and all at risk
+    // a list whose 32 slots are all at-risk rows may hide a 33rd
+    if (hm == 0xffffffffu && lane == 0) s_sat = 1;
     if (hm) {
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_count, __popc(hm));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (hit) {
         const int pos = base + __popc(hm & ((1u << lane) - 1u));
-        if (pos < a.cand_cap) out_rows[pos] = c.row;
+        if (pos < a.cand_cap) out_rows[pos] = lst[l * kList + lane].row;
       }
     }
   }
@@ -144,17 +141,14 @@ select_kernel(SelectArgs a) {
 // One CTA per query: admission floor for the full pass from the lists of the sampling pass.
 __global__ void __launch_bounds__(kSelThreads)
 seed_kernel(SeedArgs a) {
-  extern __shared__ uint32_t skey[];
-  __shared__ uint64_t scratch[33];
+  extern __shared__ uint64_t skey[];
+  __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
+  __shared__ uint64_t top[B2K_MAX_K];
   const int q = blockIdx.x;
   const int E = a.n_lists * kList;
-  const Cand* lst = a.partial + (int64_t)q * a.list_stride * kList;
-  for (int e = threadIdx.x; e < E; e += kSelThreads) {
-    const Cand c = lst[e];
-    skey[e] = c.row < 0 ? 0u : float_key(c.score);
-  }
-  __syncthreads();
-  const uint32_t bk = block_kth_key(skey, E, a.k, scratch);
+  load_list_keys(a.partial + (int64_t)q * a.list_stride * kList, E, skey);
+  block_topk_u64(skey, E, a.k, wtop, top);
+  const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
   if (threadIdx.x == 0) {
     // strictly below b_k(sample) - 2 eps <= b_k(shard) - 2 eps: rows at or under the floor are
     // never candidates, and rows above it are admitted (strict compare in the scoring epilogue)
@@ -207,7 +201,8 @@ rerank_kernel(RerankArgs a) {
 __global__ void __launch_bounds__(kSelThreads)
 finalize_kernel(FinalizeArgs a) {
   extern __shared__ uint64_t fkeys[];
-  __shared__ uint64_t scratch[33];
+  __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
+  __shared__ uint64_t top[B2K_MAX_K];
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const int flag = a.flags[q];
@@ -222,29 +217,21 @@ finalize_kernel(FinalizeArgs a) {
   for (int c = tid; c < cnt; c += kSelThreads)
     fkeys[c] = cand_key(a.cand_ip[(int64_t)q * a.cand_cap + c], a.cand_rows[(int64_t)q * a.cand_cap + c]);
   __syncthreads();
-  uint64_t prev = ~0ull;
-  const float qn2 = a.qn2[q];
-  for (int j = 0; j < a.k; ++j) {
-    uint64_t m = 0ull;
-    for (int c = tid; c < cnt; c += kSelThreads) {
-      const uint64_t v = fkeys[c];
-      if (v < prev && v > m) m = v;
+  block_topk_u64(fkeys, cnt, a.k, wtop, top);
+  if (tid < a.k) {
+    const int j = tid;
+    const uint64_t best = top[j];
+    float ip = -3.402823466e38f, dist = 3.402823466e38f;
+    int64_t lab = -1;
+    if (best != 0ull) {
+      const int32_t row = key_row(best);
+      ip = key_score(best);
+      lab = a.base_offset + row;
+      dist = fmaxf(__fmaf_rn(-2.0f, ip, __fadd_rn(a.qn2[q], a.norm2[row])), 0.f);
     }
-    const uint64_t best = block_max_u64(m, scratch);
-    prev = best == 0ull ? 0ull : best;
-    if (tid == 0) {
-      float ip = -3.402823466e38f, dist = 3.402823466e38f;
-      int64_t lab = -1;
-      if (best != 0ull) {
-        const int32_t row = key_row(best);
-        ip = key_score(best);
-        lab = a.base_offset + row;
-        dist = fmaxf(__fmaf_rn(-2.0f, ip, __fadd_rn(qn2, a.norm2[row])), 0.f);
-      }
-      if (a.out_ip) a.out_ip[(int64_t)q * a.k + j] = ip;
-      a.out_dist[(int64_t)q * a.k + j] = dist;
-      a.out_labels[(int64_t)q * a.k + j] = lab;
-    }
+    if (a.out_ip) a.out_ip[(int64_t)q * a.k + j] = ip;
+    a.out_dist[(int64_t)q * a.k + j] = dist;
+    a.out_labels[(int64_t)q * a.k + j] = lab;
   }
 }
 
@@ -295,7 +282,7 @@ merge_kernel(MergeArgs a) {
 
 // ---------------------------------------------------------------------------------------
 int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
-  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint32_t);
+  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint64_t);
   if (smem > 200 * 1024) { set_error("select: too many partial lists (%d)", a.n_lists); return B2K_E_INVALID; }
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -305,7 +292,7 @@ int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
 }
 
 int launch_seed(const SeedArgs& a, int nq, cudaStream_t st) {
-  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint32_t);
+  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint64_t);
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   seed_kernel<<<nq, kSelThreads, smem, st>>>(a);
