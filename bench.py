@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--sweep", default="", help="comma-separated extra batch sizes reported under 'sweep'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 force K-scan, 2 force K-score (debug)")
+    ap.add_argument("--hnsw-rows", type=int, default=0,
+                    help="> 0: also build the reference's HNSW (M=32, efC=200; oracle/hnsw_ref.c) on that many "
+                         "rows on the host and report recall@k / QPS for an efSearch sweep")
     ap.add_argument("--cpu-rows", type=int, default=400_000)
     ap.add_argument("--cpu-batch", type=int, default=1024)
     return ap.parse_args()
@@ -136,6 +139,34 @@ def cpu_baseline(rows: int, batch: int, k: int, reps: int = 1):
         ts.append(time.perf_counter() - t0)
     t = min(ts)
     return t, cores
+
+
+def hnsw_baseline(rows: int, k: int, nq: int = 1000):
+    """recall@k and QPS of the reference's IndexHNSWFlat(M=32, efConstruction=200) restated on the
+    host (oracle/hnsw_ref.c), against the exact ids of the same sample; efSearch sweep around the
+    reference's 64 / 50 (main/create_index.py:20-22, 336-339).  Queries are whole-vector-normalised,
+    rows have norm sqrt(3): the reference's own geometry."""
+    import numpy as np
+    import oracle
+    from oracle import cpu_flat, hnsw_ref
+    db = oracle.pack(oracle.synth_rows(DIMS, rows, total_rows=rows))["f32"]
+    q = oracle.synth_queries(DIMS, nq, rows)
+    _, exact = cpu_flat.search_flat_ip(db, q, k)
+    ix = hnsw_ref.IndexHNSWFlat(D, 32, 200, 64)
+    t0 = time.perf_counter()
+    ix.add(db)
+    build_s = time.perf_counter() - t0
+    out = {"rows": rows, "queries": nq, "M": 32, "efConstruction": 200, "build_s": build_s,
+           "cores": len(os.sched_getaffinity(0)), "kind": "port (oracle/hnsw_ref.c; faiss absent)", "efSearch": {}}
+    for ef in (16, 32, 50, 64, 128, 256):
+        ix.efSearch = ef
+        ix.search(q[:32], k)
+        t0 = time.perf_counter()
+        _, lab = ix.search(q, k)
+        dt = time.perf_counter() - t0
+        rec = float(np.mean([len(set(lab[i]) & set(exact[i])) / k for i in range(nq)]))
+        out["efSearch"][str(ef)] = {f"recall@{k}": rec, "qps": nq / dt}
+    return out
 
 
 def run_reference(args):
@@ -360,6 +391,10 @@ def main():
                "sample": f"{args.cpu_batch} queries x {args.cpu_rows} rows x D={D} fp32 in {t_cpu:.2f} s (numpy/OpenBLAS "
                          f"sgemm blocks + top-k = faiss IndexFlatIP restated); QPS scaled linearly to {n_total} rows"}
 
+    hnsw = None
+    if rank == 0 and world == 1 and args.hnsw_rows > 0:
+        hnsw = hnsw_baseline(args.hnsw_rows, k)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": B / ms_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -377,7 +412,8 @@ def main():
             "extra": {"score_ms": score_ms, "tail_ms": tail_ms, "uncertified_queries": n_unc,
                       "launches_per_step": launches, "build_rows_per_s": n_local / build_s,
                       "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * 1984) / build_s / 1e9,
-                      "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep},
+                      "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep,
+                      "hnsw_baseline": hnsw},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -117,3 +117,24 @@ def test_cpu_flat_port_agrees_with_oracle_ids():
         same = (i == lab).mean()
         assert same > 0.97
         assert np.allclose(s, ip, atol=2e-6)
+
+
+def test_hnsw_restatement_recall():
+    """The reference's IndexHNSWFlat(M=32, efC=200) restated (oracle/hnsw_ref.c): squared-L2
+    results, ascending, near-perfect recall on an easy clustered set, monotone in efSearch."""
+    from oracle import hnsw_ref
+    n = 3000
+    pk = oracle.pack(oracle.synth_rows(DIMS, n, n_clusters=16))
+    q = oracle.synth_queries(DIMS, 50, n, n_clusters=16)
+    dist, lab, _ = oracle.search_exact(pk["f32"], q, 10, pk["norm2"])
+    ix = hnsw_ref.IndexHNSWFlat(1968, 32, 200, 64)
+    ix.add(pk["f32"])
+    rec = {}
+    for ef in (10, 64):
+        ix.efSearch = ef
+        d, l = ix.search(q, 10)
+        rec[ef] = np.mean([len(set(l[i]) & set(lab[i])) / 10 for i in range(50)])
+        assert (np.diff(d, axis=1) >= 0).all()
+    assert rec[64] >= 0.95 and rec[64] >= rec[10] - 1e-9
+    same = l == lab
+    assert np.allclose(d[same], dist[same], atol=1e-4)      # METRIC_L2 values, as index.search returns
