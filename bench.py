@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--sweep", default="", help="comma-separated extra batch sizes reported under 'sweep'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: NVLink peer-memory exchange kernels (default) or NCCL all-gather + merge")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 force K-scan, 2 force K-score (debug)")
     ap.add_argument("--hnsw-rows", type=int, default=0,
                     help="> 0: also build the reference's HNSW (M=32, efC=200; oracle/hnsw_ref.c) on that many "
@@ -218,7 +220,7 @@ def main():
     import torch.distributed as dist
     import image_recommender_b200 as irb
     from image_recommender_b200 import _capi
-    from image_recommender_b200.sharded import ShardedSearcher, shard_range
+    from image_recommender_b200.sharded import PeerExchange, ShardedSearcher, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,8 +248,12 @@ def main():
 
     if args.path:
         shard.set_option(_capi.OPT_PATH, args.path)
+    exchange = None
+    if world > 1 and args.exchange == "peer":
+        max_b = max([B] + [int(x) for x in args.sweep.split(",") if x])
+        exchange = PeerExchange(local_rank, rank, world, max_entries=max_b * k)
     searcher = ShardedSearcher(lambda q, kk, out: shard.search_device(q, kk, out=out),
-                               lambda ip, d, l: irb.merge_topk_device(ip, d, l))
+                               lambda ip, d, l: irb.merge_topk_device(ip, d, l), exchange=exchange)
 
     def barrier():
         torch.cuda.synchronize()
@@ -407,10 +413,10 @@ def main():
                        "batch": B, "k": k, "rows": n_total},
             "roofline": roofline, "roofline_b1": roofline_b1, "cpu_baseline": cpu,
             "e2e": {"value": B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (launches + (1 if world > 1 else 0)),
+            "gpu_launches": args.steps * (launches + ((2 if exchange is not None else 1) if world > 1 else 0)),
             "clocks": clocks,
             "extra": {"score_ms": score_ms, "tail_ms": tail_ms, "uncertified_queries": n_unc,
-                      "launches_per_step": launches, "build_rows_per_s": n_local / build_s,
+                      "launches_per_step": launches, "exchange": (args.exchange if world > 1 else None), "build_rows_per_s": n_local / build_s,
                       "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * 1984) / build_s / 1e9,
                       "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep,
                       "hnsw_baseline": hnsw},

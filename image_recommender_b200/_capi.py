@@ -64,6 +64,12 @@ SIGNATURES = {
     "b2k_merge_topk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_void_p]),
+    "b2k_xchg_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    "b2k_xchg_destroy": (None, [C.c_void_p]),
+    "b2k_xchg_handle": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2k_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2k_xchg_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "b2k_xchg_merge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2k_normalize_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "b2k_save": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "b2k_load": (C.c_int, [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),

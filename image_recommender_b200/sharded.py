@@ -17,13 +17,73 @@ def shard_range(n_total: int, world_size: int, rank: int) -> tuple[int, int]:
     return begin, min(n_total, begin + per)
 
 
+class PeerExchange:
+    """NVLink peer-memory exchange + merge (csrc/xchg.cu): every rank stores its top-k records into
+    all ranks' receive buffers and merges locally.  Set up once per process group."""
+
+    def __init__(self, device: int, rank: int, world: int, max_entries: int = 4096 * 32, group=None,
+                 _local_peers=None):
+        import ctypes as C
+        from . import _capi
+        self._C, self._capi = C, _capi
+        self._lib = _capi.load_library()
+        self.device, self.rank, self.world = device, rank, world
+        h = C.c_void_p()
+        _capi.check(self._lib.b2k_xchg_create(device, rank, world, max_entries, C.byref(h)))
+        self._h = h
+        self._handle = (C.c_ubyte * 64)()
+        raw = C.c_void_p()
+        _capi.check(self._lib.b2k_xchg_handle(self._h, self._handle, C.byref(raw)))
+        self.raw_ptr = raw.value
+        if world > 1 and _local_peers is None:
+            import torch
+            import torch.distributed as dist
+            mine = torch.tensor(list(self._handle), dtype=torch.uint8, device=f"cuda:{device}")
+            allh = torch.empty((world, 64), dtype=torch.uint8, device=f"cuda:{device}")
+            dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+            buf = (C.c_ubyte * (64 * world)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+            _capi.check(self._lib.b2k_xchg_connect(self._h, buf, None))
+            dist.barrier(group=group)     # every rank has mapped every buffer before the first push
+
+    def connect_local(self, raw_ptrs) -> None:
+        """Ranks living in one process (tests): plain device pointers instead of IPC handles."""
+        C = self._C
+        arr = (C.c_void_p * self.world)(*raw_ptrs)
+        self._capi.check(self._lib.b2k_xchg_connect(self._h, None, arr))
+
+    def push(self, ip, dist_t, lab, stream=None) -> None:
+        import torch
+        nq, k = ip.shape
+        st = torch.cuda.current_stream(ip.device).cuda_stream if stream is None else stream
+        self._capi.check(self._lib.b2k_xchg_push(self._h, ip.data_ptr(), dist_t.data_ptr(), lab.data_ptr(), nq, k,
+                                                 self._C.c_void_p(st)))
+
+    def merge(self, nq: int, k: int, out=None, stream=None):
+        import torch
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.float32, device=dev),
+                   torch.empty((nq, k), dtype=torch.int64, device=dev),
+                   torch.empty((nq, k), dtype=torch.float32, device=dev))
+        o_d, o_l, o_ip = out
+        st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+        self._capi.check(self._lib.b2k_xchg_merge(self._h, nq, k, o_ip.data_ptr(), o_d.data_ptr(), o_l.data_ptr(),
+                                                  self._C.c_void_p(st)))
+        return o_d, o_l, o_ip
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.b2k_xchg_destroy(self._h)
+            self._h = None
+
+
 class ShardedSearcher:
     """Wraps the local shard's `search_device`; `group=None` or world size 1 means no exchange.
 
     `local_search(q, k, out)` and `merge(ip, dist, labels)` are injectable so that the
     collective plumbing can be exercised with the gloo backend on CPU tensors (tests/)."""
 
-    def __init__(self, local_search: Callable, merge: Callable, group=None):
+    def __init__(self, local_search: Callable, merge: Callable, group=None, exchange: "PeerExchange | None" = None):
         import torch.distributed as dist
         self._dist = dist
         self.local_search = local_search
@@ -32,6 +92,8 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self._send = None
         self._recv = None
+        self.exchange = exchange      # NVLink peer-memory path instead of all-gather + merge
+        self._out = None
 
     def _buffers(self, nq: int, k: int, device):
         import torch
@@ -55,6 +117,13 @@ class ShardedSearcher:
         self.local_search(q, k, (dist_t, lab, ip_t))
         if self.world == 1:
             return dist_t, lab, ip_t
+        if self.exchange is not None:
+            if self._out is None or self._out[0].shape != (nq, k):
+                self._out = (torch.empty((nq, k), dtype=torch.float32, device=q.device),
+                             torch.empty((nq, k), dtype=torch.int64, device=q.device),
+                             torch.empty((nq, k), dtype=torch.float32, device=q.device))
+            self.exchange.push(ip_t, dist_t, lab)
+            return self.exchange.merge(nq, k, out=self._out)
         self._dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
         g_lab = recv[:, :m].contiguous().view(self.world, nq, k)
         g_fl = recv[:, m:].contiguous().view(torch.float32).view(self.world, 2, nq, k)

@@ -121,6 +121,23 @@ int b2k_merge_topk_device(const float* ip, const float* dist, const int64_t* lab
                           float* out_ip, float* out_dist, int64_t* out_labels,
                           int32_t device, void* stream);
 
+/* Peer-memory exchange for the row-sharded deployment (one process per GPU of one box): each rank's
+ * final [nq, k] records are stored straight into every rank's receive buffer over NVLink (CUDA IPC
+ * mappings) and merged there — the low-latency alternative to an NCCL all-gather + K-merge.
+ *   create  -> handle (64-byte cudaIpcMemHandle_t; exchange the handles of all ranks out of band,
+ *   e.g. torch.distributed.all_gather) -> connect -> per search: push, then merge (same stream).
+ * connect(): `handles` = world x 64 bytes, or for ranks living in ONE process `raw_ptrs` = the
+ * device pointers returned through handle()'s raw_ptr.  max_entries bounds nq*k of a search. */
+typedef struct b2k_xchg b2k_xchg;
+int  b2k_xchg_create(int32_t device, int32_t rank, int32_t world, int64_t max_entries, b2k_xchg** out);
+void b2k_xchg_destroy(b2k_xchg* x);
+int  b2k_xchg_handle(b2k_xchg* x, void* handle64, void** raw_ptr);
+int  b2k_xchg_connect(b2k_xchg* x, const void* handles, const void* const* raw_ptrs);
+int  b2k_xchg_push(b2k_xchg* x, const float* ip, const float* dist, const int64_t* labels, int32_t nq,
+                   int32_t k, void* stream);
+int  b2k_xchg_merge(b2k_xchg* x, int32_t nq, int32_t k, float* out_ip, float* out_dist,
+                    int64_t* out_labels, void* stream);
+
 /* Replaces faiss.normalize_L2(x) (main/search_from_image.py:322): in place on a host
  * array, rows with zero norm untouched; computed on `device`. */
 int b2k_normalize_l2(float* x_host, int64_t n, int32_t d, int32_t device);

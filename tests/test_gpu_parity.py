@@ -348,3 +348,60 @@ def test_faiss_shim_protocol(gpu, tmp_path):
     back = faiss.read_index(str(tmp_path / "x.faiss"))
     d2, i2 = back.search(qq, 5)
     assert back.ntotal == 700 and np.array_equal(i2, wi) and np.array_equal(d2.view(np.uint32), wd.view(np.uint32))
+
+
+# ------------------------------------------------------------------- the other BASELINE configs
+@pytest.mark.parametrize("dims,n,nq,k", [
+    ([48], 10000, 1, 5),          # config 1: color-only, top-5 (the reference's own __main__ case)
+    ([1792], 6000, 200, 10),      # config 2: DreamSim-only table, query batch
+    ([32768], 1500, 1, 10),       # config 4: raw SIFT-VLAD (32768-d): beyond K-scan's row width -> tcgen05 path
+    ([32768], 1500, 3, 10),
+    ([128, 1792], 3000, 9, 10),   # a two-table combo in a non-canonical order
+])
+def test_other_baseline_configs(gpu, dims, n, nq, k):
+    irb = _irb()
+    tabs = oracle.synth_rows(dims, n, total_rows=n, n_clusters=8, abs_mask=1 if dims[0] == 48 else 0)
+    pk = oracle.pack(tabs)
+    ix = irb.FlatShard(dims, n, device=gpu)
+    ix.add_tables(tabs)
+    f, b, _ = ix.get_rows(0, n)
+    assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32)) and np.array_equal(b, pk["bf16"])
+    q = oracle.synth_queries(dims, nq, n, n_clusters=8, abs_mask=1 if dims[0] == 48 else 0)
+    st = _check(ix, pk, q, k)
+    assert st["path"] == (1 if nq == 1 and sum(dims) <= 4096 else (3 if nq > 128 else 2))
+    ix.close()
+
+
+def test_peer_exchange_two_ranks_one_process(gpu):
+    """K-exchange (csrc/xchg.cu) with both 'ranks' on one GPU in one process (plain pointers instead
+    of IPC handles).  Push and merge are separate launches, so pushing both ranks before merging
+    never makes a kernel wait for a later launch.  Three epochs exercise the double buffering."""
+    import torch
+    irb = _irb()
+    from image_recommender_b200 import _capi
+    from image_recommender_b200.sharded import PeerExchange
+    n, k, cut = 5000, 10, 2100
+    tabs, pk = _mk(n)
+    a = irb.FlatShard(DIMS, cut, device=gpu, base_offset=0)
+    b = irb.FlatShard(DIMS, n - cut, device=gpu, base_offset=cut)
+    a.add_tables([t[:cut] for t in tabs]); b.add_tables([t[cut:] for t in tabs])
+    xs = [PeerExchange(gpu, r, 2, max_entries=64 * 32, _local_peers=True) for r in range(2)]
+    for x in xs:
+        x.connect_local([y.raw_ptr for y in xs])
+    for epoch, nq in enumerate((1, 37, 64)):
+        q = oracle.synth_queries(DIMS, nq, n, n_clusters=8, qseed=50 + epoch)
+        qd = torch.from_numpy(q).cuda(gpu)
+        ra = a.search_device(qd, k)
+        rb = b.search_device(qd, k)
+        xs[0].push(ra[2], ra[0], ra[1])
+        xs[1].push(rb[2], rb[0], rb[1])
+        outs = [x.merge(nq, k) for x in xs]
+        torch.cuda.synchronize()
+        w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q, k, pk["norm2"])
+        for o_d, o_l, o_ip in outs:
+            assert np.array_equal(o_l.cpu().numpy(), w_lab)
+            assert np.array_equal(o_ip.cpu().numpy().view(np.uint32), w_ip.view(np.uint32))
+            assert np.array_equal(o_d.cpu().numpy().view(np.uint32), w_dist.view(np.uint32))
+    for x in xs:
+        x.close()
+    a.close(); b.close()
