@@ -389,6 +389,26 @@ def main():
                          "tc_frac": 2.0 * b * n_local * D / (sm * 1e-3) / 1e12 / peaks["bf16_tflops"],
                          "uncertified": un}
 
+    # ---- N > 1: the peer-memory exchange and the NCCL all-gather path must agree bit for bit
+    exchange_check = None
+    if world > 1 and exchange is not None:
+        alt = ShardedSearcher(lambda q, kk, out: shard.search_device(q, kk, out=out),
+                              lambda ip, d, l: irb.merge_topk_device(ip, d, l))
+        qc = qd[:257].contiguous()
+        a = [t.clone() for t in searcher.search_device(qc, k)]
+        b = [t.clone() for t in alt.search_device(qc, k)]
+        torch.cuda.synchronize()
+        exchange_check = bool(all(torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                                              y.view(torch.int32) if y.dtype == torch.float32 else y)
+                                  for x, y in zip(a, b)))
+        # and the alternative path's timing for the record (batch 1 and headline batch)
+        searcher_main = searcher
+        searcher = alt
+        alt_ms = {"1": time_device(q1, max(args.steps, 20), 5), str(B): time_device(qd, args.steps, args.warmup)}
+        searcher = searcher_main
+    else:
+        alt_ms = None
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t_cpu, cores = cpu_baseline(args.cpu_rows, args.cpu_batch, k)
@@ -416,7 +436,8 @@ def main():
             "gpu_launches": args.steps * (launches + ((2 if exchange is not None else 1) if world > 1 else 0)),
             "clocks": clocks,
             "extra": {"score_ms": score_ms, "tail_ms": tail_ms, "uncertified_queries": n_unc,
-                      "launches_per_step": launches, "exchange": (args.exchange if world > 1 else None), "build_rows_per_s": n_local / build_s,
+                      "launches_per_step": launches, "exchange": (args.exchange if world > 1 else None), "exchange_matches_nccl": exchange_check,
+                      "nccl_path_ms": alt_ms, "build_rows_per_s": n_local / build_s,
                       "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * 1984) / build_s / 1e9,
                       "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep,
                       "hnsw_baseline": hnsw},

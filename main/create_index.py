@@ -139,8 +139,29 @@ class FAISSIndexBuilderDB:
             yield rows
 
     # ---- decode (create_index.py:160-189) -------------------------------------------------------
-    @staticmethod
-    def _decode_blob(blob) -> np.ndarray:
+    # Fast path for the blobs the reference's extractors write (create_vector_base.py:142-145):
+    # pickle protocol 5 of a 1-D C-contiguous little-endian float32 ndarray under numpy >= 2 is
+    #   ... '_frombuffer' MEMO STACK_GLOBAL MEMO MARK BYTEARRAY8 <len:8> <raw> ... 'f4' ... '<' ... (d,) 'C' ...
+    # so the payload can be viewed in place instead of running the unpickler (4x faster per blob;
+    # the build is bound by this Python loop).  Anything else falls back to pickle.loads.
+    _FAST_MARK = b"_frombuffer\x94\x93\x94(\x96"
+    _FAST_TAIL = b"\x8c\x01C\x94t\x94R\x94."
+
+    @classmethod
+    def _decode_blob(cls, blob) -> np.ndarray:
+        if isinstance(blob, (bytes, bytearray, memoryview)) and blob[:2] == b"\x80\x05":
+            head = bytes(blob[:80])
+            m = head.find(cls._FAST_MARK)
+            if m > 0:
+                off = m + len(cls._FAST_MARK) + 8
+                n_bytes = int.from_bytes(head[off - 8:off], "little")
+                tail = bytes(blob[off + n_bytes:])
+                d = n_bytes // 4
+                shape = (b"K" + bytes([d]) if d < 256 else
+                         b"M" + d.to_bytes(2, "little") if d < 65536 else b"J" + d.to_bytes(4, "little")) + b"\x85"
+                if (n_bytes % 4 == 0 and 0 < len(tail) < 160 and b"\x8c\x02f4\x94" in tail
+                        and b"\x8c\x01<\x94" in tail and tail.endswith(shape + b"\x94" + cls._FAST_TAIL)):
+                    return np.frombuffer(blob, dtype="<f4", count=d, offset=off)
         vec = pickle.loads(blob)
         if hasattr(vec, "cpu"):
             vec = vec.cpu().numpy()

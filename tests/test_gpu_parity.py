@@ -405,3 +405,35 @@ def test_peer_exchange_two_ranks_one_process(gpu):
     for x in xs:
         x.close()
     a.close(); b.close()
+
+
+def test_config5_per_gpu_capacity_slice(gpu):
+    """BASELINE config 5 is 100 M DreamSim rows over 8 GPUs = 12.5 M x 1792 per GPU: 44.8 GB bf16 +
+    89.6 GB fp32 resident on ONE GPU (HBM-capacity sizing, 64-bit byte offsets).  Queries are noisy
+    copies of seeded rows spread over the whole shard, so rank 0 must be the source row."""
+    import torch
+    irb = _irb()
+    free, _total = torch.cuda.mem_get_info(gpu)
+    n = 12_500_000
+    need = n * 1792 * 6 + (4 << 30)
+    if free < need:
+        pytest.skip(f"needs {need >> 30} GiB free HBM, {free >> 30} GiB available")
+    ix = irb.FlatShard([1792], n, device=gpu, base_offset=87_500_000)      # the last of 8 shards
+    ix.fill_synthetic(n, total_rows=100_000_000, abs_mask=0)
+    assert ix.ntotal == n
+    # queries drawn from THIS shard's rows: sources in [base, base + n)
+    q = ix.synth_queries_device(512, total_rows=100_000_000, abs_mask=0)
+    src = np.array([oracle.synth_query_source(0x5EED, i, 100_000_000) for i in range(512)])
+    mine = (src >= 87_500_000) & (src < 100_000_000)
+    assert mine.sum() > 20
+    for m in (1, 512):
+        dist, lab, ip = ix.search_device(q[:m].contiguous(), 10)
+        torch.cuda.synchronize()
+        lab = lab.cpu().numpy()
+        assert (lab[:, 0][mine[:m]] == src[:m][mine[:m]]).all()
+        assert (lab >= 87_500_000).all() and (lab < 100_000_000).all()
+    # the last row of the shard is addressable (64-bit offsets) and finds itself
+    f, _, _ = ix.get_rows(n - 1, 1)
+    d, l = ix.search(f, 1)
+    assert l[0, 0] == 99_999_999 and d[0, 0] < 1e-5
+    ix.close()

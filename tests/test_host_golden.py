@@ -196,3 +196,32 @@ def test_build_and_search_end_to_end(workdir, gpu):
     conn = sqlite3.connect("images.db")
     assert conn.execute("SELECT offset FROM faiss_index_offsets_color_sift_dreamsim WHERE image_id = 7").fetchone()[0] == 24
     conn.close()
+
+
+def test_blob_fast_path_equals_unpickler():
+    """The in-place view of numpy float32 pickles must agree with pickle.loads on every layout the
+    tables can hold, and must fall back (not misread) on everything else."""
+    import torch
+    from main.create_index import FAISSIndexBuilderDB as B
+    rng = np.random.default_rng(3)
+    dump = lambda v: pickle.dumps(v, protocol=pickle.HIGHEST_PROTOCOL)  # noqa: E731
+    for d in (1, 48, 128, 255, 256, 1792, 32768, 70000):
+        v = rng.standard_normal(d).astype(np.float32)
+        blob = dump(v)
+        got = B._decode_blob(blob)
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), v.view(np.uint32))
+        assert np.shares_memory(got, np.frombuffer(blob, np.uint8)) or d == 0     # fast path taken
+    slow = [rng.standard_normal((1, 64)).astype(np.float32),                       # 2-D
+            rng.standard_normal(64),                                                # float64
+            rng.standard_normal(64).astype(np.float16),
+            rng.standard_normal(64).astype(">f4"),                                  # big endian
+            np.asfortranarray(rng.standard_normal((4, 16)).astype(np.float32)),
+            rng.standard_normal(128).astype(np.float32)[::2],                       # strided
+            torch.from_numpy(rng.standard_normal(64).astype(np.float32)),
+            [0.5, 1.5, 2.5]]
+    for v in slow:
+        want = np.asarray(v.cpu().numpy() if hasattr(v, "cpu") else v, dtype="float32").ravel()
+        assert np.array_equal(B._decode_blob(dump(v)), want)
+        assert np.array_equal(B._decode_blob(pickle.dumps(v, protocol=4)), want)
+    with pytest.raises(Exception):
+        B._decode_blob(b"\x80\x05not a pickle")
