@@ -95,6 +95,7 @@ struct b2k_index {
   const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
   int opt_pair = -1;                          // -1 auto (nq > 128), 0 never, 1 always
   int opt_seed = 1;                           // threshold seeding for the tcgen05 paths
+  int opt_tighten = 1;                        // exact-score tightening of the candidate threshold
   // options
   int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 1, opt_splits = 0;
   b2k_stats stats;
@@ -252,6 +253,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   se.partial = w.partial; se.n_lists = n_lists_used; se.list_stride = w.n_lists; se.k = k; se.eps = eps;
   se.cand_cap = w.cand_cap; se.force_exact = ix->opt_force_exact;
   se.cand_rows = w.cand_rows; se.cand_count = w.cand_count; se.flags = w.flags; se.thr = w.thr;
+  se.db_f32 = ix->opt_tighten ? ix->f32 : nullptr; se.q = q_dev; se.D = ix->D;
   rc = launch_select(se, nq, st);
   if (rc) return rc;
   ++launches;
@@ -284,6 +286,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   ix->ev_valid = true;
 
   ix->stats.path = path;
+  ix->stats.n_queries = nq;
   ix->stats.n_uncertified = -1;      // on the device until read back
   ix->stats.n_splits = n_lists_used;
   ix->stats.n_rerank = w.cand_cap;
@@ -554,6 +557,13 @@ int b2k_get_stats(b2k_index* ix, b2k_stats* out) {
                         cudaMemcpyDeviceToHost));
     ix->stats.eps_max = eps0;   // slack of query 0 of the last pass (representative; per-query on device)
   }
+  if (ix->ws.cand_count && ix->stats.path != 0 && ix->stats.n_queries > 0) {
+    std::vector<int32_t> cnt((size_t)ix->stats.n_queries);
+    B2K_CUDA(cudaMemcpy(cnt.data(), ix->ws.cand_count, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int64_t tot = 0;
+    for (int32_t c : cnt) tot += c;
+    ix->stats.n_candidates = (int32_t)std::min<int64_t>(tot, 0x7fffffff);
+  }
   if (ix->ev_valid) {
     float a = 0.f, b = 0.f;
     if (cudaEventElapsedTime(&a, ix->ev[0], ix->ev[1]) == cudaSuccess) ix->stats.score_ms = a;
@@ -581,6 +591,8 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
     case B2K_OPT_SPLITS:
       if (value < 0 || value > 4096) break;
       ix->opt_splits = (int)value; return 0;
+    case B2K_OPT_TIGHTEN:
+      ix->opt_tighten = value != 0; return 0;
     case B2K_OPT_SEED:
       ix->opt_seed = value != 0; return 0;
     case B2K_OPT_TC_PAIR:

@@ -67,7 +67,11 @@ struct SelectArgs {
   int32_t* cand_rows;   // [nq, cand_cap]
   int32_t* cand_count;  // [nq]
   int32_t* flags;       // [nq] 0 = certified; bit0 saturated list, bit1 overflow, bit2 forced
-  float* thr;           // [nq] candidate threshold b_k - 2 eps
+  float* thr;           // [nq] candidate threshold actually used
+  // optional tightening: exact scores of the k rows with the best approximate scores (both null = off)
+  const float* db_f32;  // [n_rows, D]
+  const float* q;       // [nq, D]
+  int32_t D;
 };
 
 struct RerankArgs {

@@ -102,7 +102,34 @@ select_kernel(SelectArgs a) {
   // listed is a candidate.
   block_topk_u64(skey, E, a.k, wtop, top);
   const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
-  const float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
+  float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
+
+  // Tightening: the k rows with the best approximate scores are k distinct rows, so the smallest of
+  // their EXACT scores s' is a lower bound of the exact k-th best score, and every row of the exact
+  // top-k has b >= s' - eps.  s' >= b_k - eps, so this threshold is never looser than b_k - 2 eps and
+  // typically one eps tighter: several times fewer rows to re-rank.  (Spec R arithmetic.)
+  if (bk != 0u && a.db_f32 != nullptr) {
+    __shared__ float s_exact[B2K_MAX_K];
+    const float* qv = a.q + (int64_t)q * a.D;
+    for (int j = warp; j < a.k; j += (kSelThreads >> 5)) {
+      const int e = E - 1 - (int)(uint32_t)(top[j] & 0xffffffffull);
+      const float* x = a.db_f32 + (int64_t)lst[e].row * a.D;
+      double p = 0.0;
+      for (int i4 = lane; i4 * 4 < a.D; i4 += 32)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = i4 * 4 + c;
+          if (i < a.D) p = __fma_rn((double)qv[i], (double)x[i], p);
+        }
+      const float sj = (float)warp_sum_f64(p);
+      if (lane == 0) s_exact[j] = sj;
+    }
+    __syncthreads();
+    float smin = INFINITY;
+    for (int j = 0; j < a.k; ++j) smin = fminf(smin, s_exact[j]);
+    const float t2 = __fsub_rd(smin, a.eps[q]);
+    if (t2 > thr) thr = t2;          // NaN-safe: keeps the looser bound
+  }
 
   // candidates + saturation, from the shared-memory keys (rows are fetched for hits only).
   // Warp w owns lists w, w+8, ...; lane j = entry j of the list.

@@ -43,6 +43,7 @@ typedef struct b2k_index b2k_index;
 #define B2K_OPT_FORCE_EXACT   3  /* 1 = treat every query as uncertified (exercise the exact fp32 scan) */
 #define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 1)    */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
+#define B2K_OPT_TIGHTEN       8  /* candidate threshold from the exact scores of the k best rows: 1 on (default) */
 #define B2K_OPT_SEED          7  /* K-score threshold seeding from a sampling pass: 1 on (default), 0 off */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs when nq > 128), 0 single CTA, 1 pairs */
 
@@ -58,6 +59,8 @@ typedef struct b2k_stats {
   float   score_ms;        /* device time of the scoring kernel(s) of the last pass (CUDA     */
                            /* events on the launching stream; the roofline numerator's clock) */
   float   tail_ms;         /* device time of select + rerank + finalize + exact of that pass  */
+  int32_t n_queries;       /* queries of the last pass                                        */
+  int32_t n_candidates;    /* rows re-ranked in fp32 over all queries of the last pass        */
 } b2k_stats;
 
 typedef struct b2k_synth {

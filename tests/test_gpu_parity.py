@@ -157,6 +157,26 @@ def test_seeded_threshold_matches_oracle_tc(db20k, path):
     _set_path(ix, "auto")
 
 
+def test_threshold_tightening_keeps_bits_and_cuts_candidates_tc(db20k):
+    """The exact-score tightening of the candidate threshold (select_kernel) re-ranks fewer rows and
+    returns the same bits."""
+    from image_recommender_b200 import _capi
+    ix, pk, n = db20k
+    q = oracle.synth_queries(DIMS, 40, n, n_clusters=8, qseed=4242)
+    cands = {}
+    for path in ("scan", "tc2"):
+        _set_path(ix, path)
+        for on in (0, 1):
+            ix.set_option(_capi.OPT_TIGHTEN, on)
+            st = _check(ix, pk, q[:4] if path == "scan" else q, 10)
+            cands[(path, on)] = st["n_candidates"] / st["n_queries"]
+            assert st["n_uncertified"] == 0
+    ix.set_option(_capi.OPT_TIGHTEN, 1)
+    _set_path(ix, "auto")
+    assert cands[("tc2", 1)] < 0.7 * cands[("tc2", 0)] and cands[("scan", 1)] < cands[("scan", 0)]
+    assert cands[("tc2", 1)] >= 10
+
+
 def test_search_auto_path_and_fallback_tc(db20k):
     from image_recommender_b200 import _capi
     ix, pk, n = db20k
