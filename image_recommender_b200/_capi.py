@@ -15,7 +15,7 @@ B2K_MAX_TABLES = 8
 B2K_MAX_K = 32
 B2K_LIST = 32
 
-OPT_PATH, OPT_RERANK, OPT_FORCE_EXACT, OPT_SCAN_MAX_B, OPT_SPLITS, OPT_TC_PAIR, OPT_SEED, OPT_TIGHTEN = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_PATH, OPT_RERANK, OPT_FORCE_EXACT, OPT_SCAN_MAX_B, OPT_SPLITS, OPT_TC_PAIR, OPT_SEED, OPT_TIGHTEN, OPT_COLLECT = 1, 2, 3, 4, 5, 6, 7, 8, 9
 PATH_AUTO, PATH_SCAN, PATH_TC = 0, 1, 2
 E_INVALID, E_CAPACITY, E_IO, E_NODEVICE, E_NOMEM = -1, -2, -3, -4, -5
 
@@ -30,7 +30,8 @@ class Stats(C.Structure):
     _fields_ = [("path", C.c_int32), ("n_splits", C.c_int32), ("n_rerank", C.c_int32),
                 ("n_uncertified", C.c_int32), ("eps_max", C.c_float), ("err_max", C.c_float),
                 ("norm_max", C.c_float), ("launches", C.c_int32), ("score_ms", C.c_float),
-                ("tail_ms", C.c_float), ("n_queries", C.c_int32), ("n_candidates", C.c_int32)]
+                ("tail_ms", C.c_float), ("n_queries", C.c_int32), ("n_candidates", C.c_int32),
+                ("n_saturated", C.c_int32)]
 
 
 class Synth(C.Structure):

@@ -53,7 +53,9 @@ struct Workspace {
   int nq_cap = 0, n_lists = 0, cand_cap = 0, exact_splits = 0;
   float* q = nullptr;             // [nq, D] staging for the host API
   uint16_t* q_bf16 = nullptr;     // [nq_pad, Dp]
-  float *qn2 = nullptr, *eps_scan = nullptr, *eps_tc = nullptr, *thr = nullptr, *thr_floor = nullptr;
+  float *qn2 = nullptr, *eps_scan = nullptr, *eps_tc = nullptr, *thr = nullptr, *thr_floor = nullptr, *lb = nullptr;
+  int2* sat_pairs = nullptr;      // [sat_cap] saturated (query, list) pairs of the last pass (K-collect's work list)
+  int sat_cap = 0;
   Cand* partial = nullptr;        // [nq, n_lists, 32]
   int32_t *cand_rows = nullptr, *cand_count = nullptr, *flags = nullptr;
   float* cand_ip = nullptr;
@@ -63,6 +65,7 @@ struct Workspace {
   int64_t* out_labels = nullptr;
   void release() {
     dev_free(q); dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr); dev_free(thr_floor);
+    dev_free(lb); dev_free(sat_pairs);
     dev_free(partial); dev_free(cand_rows); dev_free(cand_count); dev_free(flags); dev_free(cand_ip);
     dev_free(fail_count); dev_free(fail_list); dev_free(exact_partial);
     dev_free(out_ip); dev_free(out_dist); dev_free(out_labels);
@@ -96,6 +99,7 @@ struct b2k_index {
   int opt_pair = -1;                          // -1 auto (nq > 128), 0 never, 1 always
   int opt_seed = 1;                           // threshold seeding for the tcgen05 paths
   int opt_tighten = 1;                        // exact-score tightening of the candidate threshold
+  int opt_collect = 1;                        // K-collect serves saturated lists (else: exhaustive scan)
   // options
   int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 1, opt_splits = 0;
   b2k_stats stats;
@@ -150,12 +154,15 @@ int ensure_workspace(b2k_index* ix, int nq) {
   if ((rc = dev_alloc(&w.eps_tc, cap))) return rc;
   if ((rc = dev_alloc(&w.thr, cap))) return rc;
   if ((rc = dev_alloc(&w.thr_floor, cap))) return rc;
+  if ((rc = dev_alloc(&w.lb, cap))) return rc;
+  w.sat_cap = 1024 + 2 * cap;
+  if ((rc = dev_alloc(&w.sat_pairs, (size_t)w.sat_cap))) return rc;
   if ((rc = dev_alloc(&w.partial, (size_t)cap * n_lists * kList))) return rc;
   if ((rc = dev_alloc(&w.cand_rows, (size_t)cap * cand_cap))) return rc;
   if ((rc = dev_alloc(&w.cand_ip, (size_t)cap * cand_cap))) return rc;
   if ((rc = dev_alloc(&w.cand_count, cap))) return rc;
   if ((rc = dev_alloc(&w.flags, cap))) return rc;
-  if ((rc = dev_alloc(&w.fail_count, 1))) return rc;
+  if ((rc = dev_alloc(&w.fail_count, 2))) return rc;      // [0] failed queries, [1] saturated pairs
   if ((rc = dev_alloc(&w.fail_list, cap))) return rc;
   if ((rc = dev_alloc(&w.exact_partial, (size_t)cap * exact_splits * kList))) return rc;
   if ((rc = dev_alloc(&w.out_ip, (size_t)cap * B2K_MAX_K))) return rc;
@@ -186,9 +193,9 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   int rc = launch_query_prep(qp, st);
   if (rc) return rc;
   ++launches;
-  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, sizeof(int32_t), st));
+  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, 2 * sizeof(int32_t), st));
 
-  int n_lists_used = 0;
+  int n_lists_used = 0, split_tile_rows = 0;
   const float* eps = nullptr;
   B2K_CUDA(cudaEventRecord(ix->ev[0], st));
   if (path == 1) {
@@ -226,8 +233,12 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // k-th best score from below, so the full pass admits only rows that can still matter and
     // the fused selection stops being the epilogue's bottleneck (DESIGN.md "seeding").
     const int64_t tiles_total = (ix->ntotal + 255) / 256;
-    const bool seed = ix->opt_seed && tiles_total >= (int64_t)16 * ta.plan.n_splits;
-    const int sample_tiles = tiles_total >= (int64_t)96 * ta.plan.n_splits ? 2 : 1;   // <= ~3 % extra work
+    const int64_t tiles_per_split = tiles_total / ta.plan.n_splits;
+    const bool seed = ix->opt_seed && tiles_per_split >= 16;
+    // sample ~0.75 % of the shard whatever the split count: a smaller sample leaves the floor too low
+    // (more list insertions in the main pass), a larger one costs more than it saves
+    int sample_tiles = ix->opt_seed > 1 ? ix->opt_seed : (int)((tiles_per_split * 3 + 200) / 400);
+    sample_tiles = (int)std::max<int64_t>(1, std::min<int64_t>(sample_tiles, tiles_per_split / 8));
     if (seed) {
       ta.max_tiles = sample_tiles;
       rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
@@ -245,6 +256,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     ++launches;
     path = pair ? 3 : 2;
     n_lists_used = ta.plan.n_splits;
+    split_tile_rows = score_tc_tile_rows();
     eps = w.eps_tc;
   }
   B2K_CUDA(cudaEventRecord(ix->ev[1], st));
@@ -254,9 +266,22 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   se.cand_cap = w.cand_cap; se.force_exact = ix->opt_force_exact;
   se.cand_rows = w.cand_rows; se.cand_count = w.cand_count; se.flags = w.flags; se.thr = w.thr;
   se.db_f32 = ix->opt_tighten ? ix->f32 : nullptr; se.q = q_dev; se.D = ix->D;
+  se.lb = w.lb; se.sat_count = w.fail_count + 1; se.sat_pairs = ix->opt_collect ? w.sat_pairs : nullptr;
+  se.sat_cap = ix->opt_collect ? w.sat_cap : 0;
   rc = launch_select(se, nq, st);
   if (rc) return rc;
   ++launches;
+
+  if (ix->opt_collect) {
+    CollectArgs ca;
+    ca.db = ix->bf16; ca.n_rows = ix->ntotal; ca.D = ix->D; ca.Dp = ix->Dp; ca.q = q_dev; ca.lb = w.lb;
+    ca.eps = w.eps_scan; ca.sat_count = w.fail_count + 1; ca.sat_pairs = w.sat_pairs; ca.sat_cap = w.sat_cap;
+    ca.n_splits = n_lists_used; ca.tile_rows = split_tile_rows;
+    ca.cand_rows = w.cand_rows; ca.cand_count = w.cand_count; ca.flags = w.flags; ca.cand_cap = w.cand_cap;
+    rc = launch_collect(ca, ix->n_sm, st);
+    if (rc) return rc;
+    ++launches;
+  }
 
   RerankArgs rr;
   rr.db_f32 = ix->f32; rr.q = q_dev; rr.cand_rows = w.cand_rows; rr.cand_count = w.cand_count;
@@ -557,11 +582,16 @@ int b2k_get_stats(b2k_index* ix, b2k_stats* out) {
                         cudaMemcpyDeviceToHost));
     ix->stats.eps_max = eps0;   // slack of query 0 of the last pass (representative; per-query on device)
   }
+  if (ix->ws.fail_count && ix->stats.path != 0) {
+    int32_t ns = 0;
+    B2K_CUDA(cudaMemcpy(&ns, ix->ws.fail_count + 1, sizeof(ns), cudaMemcpyDeviceToHost));
+    ix->stats.n_saturated = ns;
+  }
   if (ix->ws.cand_count && ix->stats.path != 0 && ix->stats.n_queries > 0) {
     std::vector<int32_t> cnt((size_t)ix->stats.n_queries);
     B2K_CUDA(cudaMemcpy(cnt.data(), ix->ws.cand_count, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     int64_t tot = 0;
-    for (int32_t c : cnt) tot += c;
+    for (int32_t c : cnt) tot += std::min(c, ix->ws.cand_cap);
     ix->stats.n_candidates = (int32_t)std::min<int64_t>(tot, 0x7fffffff);
   }
   if (ix->ev_valid) {
@@ -593,8 +623,11 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
       ix->opt_splits = (int)value; return 0;
     case B2K_OPT_TIGHTEN:
       ix->opt_tighten = value != 0; return 0;
+    case B2K_OPT_COLLECT:
+      ix->opt_collect = value != 0; return 0;
     case B2K_OPT_SEED:
-      ix->opt_seed = value != 0; return 0;
+      if (value < 0 || value > 4096) break;
+      ix->opt_seed = (int)value; return 0;
     case B2K_OPT_TC_PAIR:
       if (value < -1 || value > 1) break;
       ix->opt_pair = (int)value; return 0;

@@ -66,12 +66,38 @@ struct SelectArgs {
   int32_t force_exact;
   int32_t* cand_rows;   // [nq, cand_cap]
   int32_t* cand_count;  // [nq]
-  int32_t* flags;       // [nq] 0 = certified; bit0 saturated list, bit1 overflow, bit2 forced
+  int32_t* flags;       // [nq] 0 = certified; bit0 saturated list not handed to K-collect, bit1 overflow, bit2 forced
   float* thr;           // [nq] candidate threshold actually used
+  float* lb;            // [nq] lower bound of the exact k-th best score (K-collect derives its own threshold)
+  // saturated (query, list) pairs are handed to K-collect instead of failing the query (null = off)
+  int32_t* sat_count;   // [1]
+  int2* sat_pairs;      // [sat_cap] (query, list)
+  int32_t sat_cap;
   // optional tightening: exact scores of the k rows with the best approximate scores (both null = off)
   const float* db_f32;  // [n_rows, D]
   const float* q;       // [nq, D]
   int32_t D;
+};
+
+// K-collect: re-scan of the DB splits whose partial list was saturated (every one of its 32 entries
+// at or above the candidate threshold, so it may hide more): EVERY row of such a split whose
+// approximate score reaches the threshold becomes a re-rank candidate.
+struct CollectArgs {
+  const uint16_t* db;   // bf16 [n_rows, Dp]
+  int64_t n_rows;
+  int32_t D, Dp;
+  const float* q;       // fp32 [nq, D]
+  const float* lb;      // [nq] lower bound of the exact k-th best score (from K-select)
+  const float* eps;     // [nq] |fp32 query x bf16 row - exact| bound (the K-scan bound)
+  const int32_t* sat_count;
+  const int2* sat_pairs;
+  int32_t sat_cap;
+  int32_t n_splits;     // splits of the scoring pass that filled the lists
+  int32_t tile_rows;    // 0: split s = rows [n*s/S, n*(s+1)/S) (K-scan); else tiles of that many rows (K-score)
+  int32_t* cand_rows;   // [nq, cand_cap]
+  int32_t* cand_count;  // [nq] appended to
+  int32_t* flags;       // [nq] bit1 set on overflow
+  int32_t cand_cap;
 };
 
 struct RerankArgs {
@@ -132,6 +158,7 @@ bool scan_supports(int Dp);
 int launch_scan(const ScanArgs& a, int n_queries_this_pass, cudaStream_t st);
 
 int launch_select(const SelectArgs& a, int nq, cudaStream_t st);
+int launch_collect(const CollectArgs& a, int n_sm, cudaStream_t st);
 int launch_rerank(const RerankArgs& a, int n_sm, cudaStream_t st);
 int launch_finalize(const FinalizeArgs& a, cudaStream_t st);
 int exact_num_splits(int n_sm);
@@ -165,6 +192,7 @@ struct SeedArgs {
 };
 int launch_seed(const SeedArgs& a, int nq, cudaStream_t st);
 bool score_tc_supports(int Dp);
+int score_tc_tile_rows();      // DB rows per accumulator tile: split boundaries are multiples of it
 ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits);
 int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_bf16, int nq_pad,
                          const uint16_t* db_bf16, int64_t n_rows, int Dp);

@@ -239,6 +239,86 @@ int launch_scan(const ScanArgs& a, int nq_pass, cudaStream_t st) {
 }
 
 // =========================================================================================
+// K-collect: second look at the DB splits whose partial list was saturated for a query (K-select
+// found all 32 entries at or above the candidate threshold, so the list may hide more such rows —
+// the usual cause is a run of near-duplicate images stored next to each other).  The split is
+// re-scored for that query alone (fp32 query x bf16 rows, fp32 accumulation: the K-scan arithmetic
+// class, bound eps) and EVERY row with score >= lb - eps is appended to the query's re-rank
+// candidates, where lb <= exact k-th best score.  A row of the exact top-k has exact score >= lb,
+// hence approximate score >= lb - eps: none is missed, and the query stays certified.  Only a
+// candidate-buffer overflow (thousands of near-ties) still needs the exhaustive K-exact scan.
+// Work items = (pair, 1/kCollectSub of its split), one warp per row; launched unconditionally and
+// exits at once when no list was saturated.
+namespace {
+constexpr int kCollectSub = 64;
+constexpr int kCollectWarps = 8;
+}  // namespace
+
+__global__ void __launch_bounds__(kCollectWarps * 32)
+collect_kernel(CollectArgs a) {
+  const int n_pairs = min(*a.sat_count, a.sat_cap);
+  if (n_pairs == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_chunks = a.Dp >> 3;
+  const int64_t tiles_total = a.tile_rows > 0 ? (a.n_rows + a.tile_rows - 1) / a.tile_rows : 0;
+  for (int64_t w = blockIdx.x; w < (int64_t)n_pairs * kCollectSub; w += gridDim.x) {
+    const int2 pr = a.sat_pairs[w / kCollectSub];
+    const int sub = (int)(w % kCollectSub);
+    const int q = pr.x, split = pr.y;
+    int64_t r_begin, r_end;
+    if (a.tile_rows > 0) {
+      r_begin = (tiles_total * split / a.n_splits) * a.tile_rows;
+      r_end = min(a.n_rows, (tiles_total * (split + 1) / a.n_splits) * a.tile_rows);
+    } else {
+      r_begin = a.n_rows * (int64_t)split / a.n_splits;
+      r_end = a.n_rows * (int64_t)(split + 1) / a.n_splits;
+    }
+    const int64_t len = r_end - r_begin;
+    const int64_t s0 = r_begin + len * sub / kCollectSub, s1 = r_begin + len * (sub + 1) / kCollectSub;
+    const float thr = __fsub_rd(a.lb[q], a.eps[q]);
+    if (!(thr == thr)) {     // poisoned bound (NaN rows in the shard): only the exhaustive scan is safe
+      if (threadIdx.x == 0) atomicOr(a.flags + q, 1);
+      continue;
+    }
+    const float* __restrict__ qv = a.q + (int64_t)q * a.D;
+    const bool qvec = ((a.D & 7) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 15) == 0);
+    for (int64_t row = s0 + warp; row < s1; row += kCollectWarps) {
+      const uint4* __restrict__ x = reinterpret_cast<const uint4*>(a.db + row * a.Dp);
+      float acc = 0.f;
+      for (int c = lane; c < n_chunks; c += 32) {
+        const uint4 v = __ldcs(x + c);
+        float qf[8];
+        if (qvec && c * 8 < a.D) {
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * c);
+          const float4 q1 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * c + 1);
+          qf[0] = q0.x; qf[1] = q0.y; qf[2] = q0.z; qf[3] = q0.w;
+          qf[4] = q1.x; qf[5] = q1.y; qf[6] = q1.z; qf[7] = q1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const int i = c * 8 + j; qf[j] = i < a.D ? __ldg(qv + i) : 0.f; }
+        }
+        acc = fmaf(__uint_as_float(v.x << 16), qf[0], acc); acc = fmaf(__uint_as_float(v.x & 0xffff0000u), qf[1], acc);
+        acc = fmaf(__uint_as_float(v.y << 16), qf[2], acc); acc = fmaf(__uint_as_float(v.y & 0xffff0000u), qf[3], acc);
+        acc = fmaf(__uint_as_float(v.z << 16), qf[4], acc); acc = fmaf(__uint_as_float(v.z & 0xffff0000u), qf[5], acc);
+        acc = fmaf(__uint_as_float(v.w << 16), qf[6], acc); acc = fmaf(__uint_as_float(v.w & 0xffff0000u), qf[7], acc);
+      }
+      acc = warp_sum_f32(acc);
+      if (lane == 0 && acc >= thr) {
+        const int pos = atomicAdd(a.cand_count + q, 1);
+        if (pos < a.cand_cap) a.cand_rows[(int64_t)q * a.cand_cap + pos] = (int32_t)row;
+        else atomicOr(a.flags + q, 2);
+      }
+    }
+  }
+}
+
+int launch_collect(const CollectArgs& a, int n_sm, cudaStream_t st) {
+  collect_kernel<<<4 * n_sm, kCollectWarps * 32, 0, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+// =========================================================================================
 // K-exact: exhaustive fp32 scan with fp64 accumulation (Spec R) for uncertified queries.
 // One warp per row, up to 4 failed queries per sweep, warp-private top-32 in registers
 // (one entry per lane), merged per CTA at the end.  Launched unconditionally; exits at once

@@ -145,6 +145,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------
+int score_tc_tile_rows() { return kBlockN; }
 bool score_tc_supports(int Dp) { return Dp >= kBlockK && (Dp % kBlockK) == 0; }
 
 ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) {

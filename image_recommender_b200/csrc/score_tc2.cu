@@ -154,7 +154,24 @@ ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) 
   ScoreTcPlan p;
   p.n_qtiles = (nq + 2 * kBlockM - 1) / (2 * kBlockM);
   const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
-  int splits = forced_splits > 0 ? forced_splits : n_sm;
+  // One CTA pair per two SMs is resident at a time, so the grid runs in waves of n_sm/2 pairs and every
+  // CTA pays one pipeline fill + one un-overlapped last epilogue (about 1.5 tile times).  With >= 128
+  // tiles per CTA that is noise and more, shorter CTAs balance better (10 M rows: 148 splits best);
+  // on small shards fewer splits win (1.25 M rows: 37 instead of 148 splits is +8 % at batch 4096,
+  // +10 % at batch 512; gpurun_out/exp_splits.log).  Only split counts that keep
+  // n_qtiles * n_splits a whole number of waves are considered.
+  int splits = n_sm;
+  if (forced_splits > 0) {
+    splits = forced_splits;
+  } else {
+    const int wave = n_sm / 2 > 0 ? n_sm / 2 : 1;
+    for (int div = 1; div <= 4; div <<= 1) {
+      const int s = n_sm / div;
+      if (s < 1 || n_sm % div != 0 || ((int64_t)p.n_qtiles * s) % wave != 0) continue;
+      splits = s;
+      if (tiles_total / s >= 128) break;
+    }
+  }
   if ((int64_t)splits > tiles_total) splits = (int)(tiles_total > 0 ? tiles_total : 1);
   p.n_splits = splits;
   p.grid = 2 * p.n_qtiles * p.n_splits;

@@ -103,6 +103,8 @@ select_kernel(SelectArgs a) {
   block_topk_u64(skey, E, a.k, wtop, top);
   const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
   float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
+  // lower bound of the exact k-th best score: the k best approximate rows have exact >= b_k - eps
+  float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
 
   // Tightening: the k rows with the best approximate scores are k distinct rows, so the smallest of
   // their EXACT scores s' is a lower bound of the exact k-th best score, and every row of the exact
@@ -128,7 +130,7 @@ select_kernel(SelectArgs a) {
     float smin = INFINITY;
     for (int j = 0; j < a.k; ++j) smin = fminf(smin, s_exact[j]);
     const float t2 = __fsub_rd(smin, a.eps[q]);
-    if (t2 > thr) thr = t2;          // NaN-safe: keeps the looser bound
+    if (t2 > thr) { thr = t2; lb = smin; }      // NaN-safe: keeps the looser bound
   }
 
   // candidates + saturation, from the shared-memory keys (rows are fetched for hits only).
@@ -140,8 +142,17 @@ select_kernel(SelectArgs a) {
     const uint32_t sk = (uint32_t)(key >> 32);
     const bool hit = sk != 0u && sk >= thr_key;
     const unsigned hm = __ballot_sync(0xffffffffu, hit);
-    // a list whose 32 slots are all at-risk rows may hide a 33rd
-    if (hm == 0xffffffffu && lane == 0) s_sat = 1;
+    // a list whose 32 slots are all at-risk rows may hide a 33rd: K-collect re-scans that DB split
+    // for this query and lists EVERY row at or above the threshold (so nothing is emitted here);
+    // only when the pair table is full does the query fall back to the exhaustive scan
+    if (hm == 0xffffffffu) {
+      if (lane == 0) {
+        const int slot = a.sat_pairs ? atomicAdd(a.sat_count, 1) : a.sat_cap;
+        if (slot < a.sat_cap) a.sat_pairs[slot] = make_int2(q, l);
+        else s_sat = 1;
+      }
+      if (a.sat_pairs) continue;     // on pair-table overflow the query is flagged: its candidates are unused
+    }
     if (hm) {
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_count, __popc(hm));
@@ -162,6 +173,7 @@ select_kernel(SelectArgs a) {
     a.cand_count[q] = cnt;
     a.flags[q] = flag;
     a.thr[q] = thr;
+    a.lb[q] = lb;
   }
 }
 
@@ -188,7 +200,7 @@ seed_kernel(SeedArgs a) {
 __global__ void __launch_bounds__(256)
 rerank_kernel(RerankArgs a) {
   const int q = blockIdx.y;
-  const int cnt = a.cand_count[q];
+  const int cnt = min(a.cand_count[q], a.cand_cap);    // K-collect may have counted past the capacity
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int w0 = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -240,7 +252,7 @@ finalize_kernel(FinalizeArgs a) {
     }
     return;   // K-exact writes this query's outputs
   }
-  const int cnt = a.cand_count[q];
+  const int cnt = min(a.cand_count[q], a.cand_cap);
   for (int c = tid; c < cnt; c += kSelThreads)
     fkeys[c] = cand_key(a.cand_ip[(int64_t)q * a.cand_cap + c], a.cand_rows[(int64_t)q * a.cand_cap + c]);
   __syncthreads();

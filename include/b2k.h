@@ -44,7 +44,8 @@ typedef struct b2k_index b2k_index;
 #define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 1)    */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
 #define B2K_OPT_TIGHTEN       8  /* candidate threshold from the exact scores of the k best rows: 1 on (default) */
-#define B2K_OPT_SEED          7  /* K-score threshold seeding from a sampling pass: 1 on (default), 0 off */
+#define B2K_OPT_COLLECT       9  /* saturated partial lists are re-scanned by K-collect: 1 on (default), 0 = exhaustive scan */
+#define B2K_OPT_SEED          7  /* K-score threshold seeding from a sampling pass: 1 auto (default), 0 off, N > 1 = N sample tiles per split */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs when nq > 128), 0 single CTA, 1 pairs */
 
 typedef struct b2k_stats {
@@ -61,6 +62,8 @@ typedef struct b2k_stats {
   float   tail_ms;         /* device time of select + rerank + finalize + exact of that pass  */
   int32_t n_queries;       /* queries of the last pass                                        */
   int32_t n_candidates;    /* rows re-ranked in fp32 over all queries of the last pass        */
+  int32_t n_saturated;     /* (query, DB split) pairs whose partial list was full of candidates */
+                           /* in the last pass: re-scanned by K-collect                        */
 } b2k_stats;
 
 typedef struct b2k_synth {

@@ -151,7 +151,7 @@ def test_seeded_threshold_matches_oracle_tc(db20k, path):
         for seed in (1, 0):
             ix.set_option(_capi.OPT_SEED, seed)
             st = _check(ix, pk, q, k)
-            assert st["launches"] == (9 if seed else 7)
+            assert st["launches"] == (10 if seed else 8)
     ix.set_option(_capi.OPT_SEED, 1)
     ix.set_option(_capi.OPT_SPLITS, 0)
     _set_path(ix, "auto")
@@ -244,19 +244,54 @@ def test_empty_index_returns_padding(gpu):
 
 
 def test_duplicate_rows_tie_break_by_offset_tc(gpu):
-    """Exact-score ties (duplicate images) are ordered by lower offset, on both paths."""
+    """Exact-score ties (duplicate images) are ordered by lower offset, on every path.  41 identical
+    rows saturate a partial list (32 entries): K-collect re-scans that DB split and the query stays
+    certified; with K-collect off the same bits come from the exhaustive scan."""
     irb = _irb()
     from image_recommender_b200 import _capi
     tabs, _ = _mk(600)
     for t in tabs:
-        t[100:140] = t[7]                 # 41 identical rows: more than one partial list holds
+        t[100:141] = t[7]                 # 42 identical rows: more than one partial list holds
     pk = oracle.pack(tabs)
     ix = irb.FlatShard(DIMS, 600, device=gpu)
     ix.add_tables(tabs)
     q = oracle.normalize_l2(pk["f32"][[7, 120]])
     for path in ("scan", "tc", "tc2"):
         _set_path(ix, path)
-        _check(ix, pk, q, 32)
+        ix.set_option(_capi.OPT_SPLITS, 0 if path == "scan" else 1)     # one split: its list must saturate
+        for collect in (1, 0):
+            ix.set_option(_capi.OPT_COLLECT, collect)
+            st = _check(ix, pk, q, 32)
+            if path != "scan":
+                assert st["n_saturated"] == (2 if collect else 0)
+                assert st["n_uncertified"] == (0 if collect else 2)
+    ix.close()
+
+
+@pytest.mark.parametrize("path", ["scan", "tc", "tc2"])
+def test_near_duplicate_runs_are_collected(gpu, path):
+    """A burst of 300 near-identical images stored next to each other (one DB split) and a second
+    burst of 5000 (more than the candidate buffer holds): the first is served by K-collect, the
+    second overflows into the exhaustive scan; both return the oracle's bits."""
+    irb = _irb()
+    from image_recommender_b200 import _capi
+    n = 9000
+    tabs, _ = _mk(n)
+    rng = np.random.default_rng(5)
+    for t in tabs:
+        t[1000:1300] = t[1000] + 1e-4 * rng.standard_normal((300, t.shape[1])).astype(np.float32)
+        t[3000:8000] = t[3000]
+    pk = oracle.pack(tabs)
+    ix = irb.FlatShard(DIMS, n, device=gpu)
+    ix.add_tables(tabs)
+    _set_path(ix, path)
+    q = oracle.normalize_l2(pk["f32"][[1100, 17, 3500]])
+    st = _check(ix, pk, q, 10)
+    assert st["n_saturated"] >= 2            # both bursts saturate at least one list
+    assert st["n_uncertified"] == 1          # only the 5000-row burst needs the exhaustive scan
+    q1 = oracle.normalize_l2(pk["f32"][[1100, 17]])
+    st = _check(ix, pk, q1, 10)
+    assert st["n_saturated"] >= 1 and st["n_uncertified"] == 0
     ix.close()
 
 
