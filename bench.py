@@ -29,6 +29,36 @@ D = sum(DIMS)
 METRIC = "QPS @top-10 exact kNN, 10M combo vecs"
 UNIT = "queries/s"
 
+# BASELINE.json `configs`.  "3" is the headline the driver runs; the others are
+# side workloads for `--config`.  per_gpu: the config only fits a box of 8, so with fewer GPUs the
+# database is cut to that many rows per GPU (weak scaling; the row count used is in the JSON line).
+CONFIGS = {
+    "2": dict(dims=[1792], rows=1_000_000, batch=1000, per_gpu=None, name="DreamSim-only (1792)"),
+    "3": dict(dims=[48, 128, 1792], rows=10_000_000, batch=4096, per_gpu=None,
+              name="combo color+sift+dreamsim (48+128+1792)"),
+    "4": dict(dims=[32768], rows=5_000_000, batch=1, per_gpu=625_000, name="SIFT-VLAD raw descriptor (32768)"),
+    "4s": dict(dims=[128], rows=5_000_000, batch=1, per_gpu=None, name="SIFT-VLAD as stored (128)"),
+    "5": dict(dims=[1792], rows=100_000_000, batch=1, per_gpu=12_500_000, name="DreamSim 100M (1792)"),
+}
+
+
+def apply_config(args):
+    """Resolve --config into dims / rows / batch (explicit --rows / --batch win)."""
+    global DIMS, D, METRIC
+    c = CONFIGS[args.config]
+    DIMS, D = list(c["dims"]), sum(c["dims"])
+    rows = c["rows"]
+    if c["per_gpu"]:
+        rows = min(rows, c["per_gpu"] * max(args.gpus, 1))
+    if args.rows is None:
+        args.rows = rows
+    if args.batch is None:
+        args.batch = c["batch"]
+    args.workload_name = c["name"]
+    args.scaling = "weak" if c["per_gpu"] and rows < c["rows"] else "strong"
+    if args.config != "3":
+        METRIC = f"QPS @top-{args.k} exact kNN, {args.rows} {c['name']} vecs (BASELINE config {args.config})"
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -36,8 +66,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=10_000_000, help="total database rows over all ranks")
-    ap.add_argument("--batch", type=int, default=4096, help="queries per step (headline)")
+    ap.add_argument("--config", default="3", choices=sorted(CONFIGS), help="BASELINE.json config (default 3: the headline)")
+    ap.add_argument("--rows", type=int, default=None, help="total database rows over all ranks (default: the config's)")
+    ap.add_argument("--batch", type=int, default=None, help="queries per step (default: the config's; 4096 for config 3)")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--sweep", default="", help="comma-separated extra batch sizes reported under 'sweep'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -49,7 +80,9 @@ def parse_args():
                          "rows on the host and report recall@k / QPS for an efSearch sweep")
     ap.add_argument("--cpu-rows", type=int, default=400_000)
     ap.add_argument("--cpu-batch", type=int, default=1024)
-    return ap.parse_args()
+    args = ap.parse_args()
+    apply_config(args)
+    return args
 
 
 def load_traffic(kernel: str, rows_local: int, batch: int):
@@ -178,6 +211,7 @@ def run_reference(args):
     if rank != 0:
         return
     rows, batch = args.cpu_rows, args.cpu_batch
+    rows = max(1024, min(rows, int(rows * 1968 / D)))      # same host memory whatever the row width
     import numpy as np
     import oracle
     from oracle import cpu_flat
@@ -200,8 +234,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * (args.rows / rows) * (args.batch / batch),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"combo color+sift+dreamsim D={D}, {args.rows} rows, batch {args.batch}, top-{args.k}",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload_name} D={D}, {args.rows} rows, batch {args.batch}, top-{args.k}",
                    "sample": sample},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -235,6 +269,7 @@ def main():
     peaks = load_peaks()
 
     n_total, B, k = args.rows, args.batch, args.k
+    Dp = (D + 63) // 64 * 64
     r0, r1 = shard_range(n_total, world, rank)
     n_local = r1 - r0
 
@@ -340,6 +375,12 @@ def main():
                 "kernel": kname,
                 "kernel_ms": score_ms, "peak_source": peaks["source"] + " burst (kernel timed alone per step)",
                 "algorithmic_flops_per_launch": flops}
+    if B <= 128:     # small headline batch (configs 4, 5): the scoring kernel is HBM-bound
+        ach = 2.0 * n_local * D / (score_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": load_traffic(kname, n_local, B), "kernel": kname,
+                    "kernel_ms": score_ms, "peak_source": peaks["source"] + " copy bandwidth",
+                    "algorithmic_bytes_per_launch": 2.0 * n_local * D}
 
     # ---- batch-1 (HBM-bound) leg, reported alongside
     q1 = qd[:1].contiguous()
@@ -359,6 +400,7 @@ def main():
     pack = None
     if rank == 0:
         n_pack, reps = 131072, 6
+        n_pack = max(1024, min(n_pack, int(n_pack * 1968 / D)))
         scratch = irb.FlatShard(DIMS, n_pack * (reps + 2), device=local_rank)
         tabs = [torch.randn((n_pack, d), device=dev, dtype=torch.float32) for d in DIMS]
         for _ in range(2):
@@ -371,7 +413,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms_pack = e0.elapsed_time(e1) / reps
-        bytes_pack = n_pack * (4.0 * D + 4.0 * D + 2.0 * 1984 + 4.0)     # read fp32, write fp32 + bf16 + norm
+        bytes_pack = n_pack * (4.0 * D + 4.0 * D + 2.0 * Dp + 4.0)       # read fp32, write fp32 + bf16 + norm
         pack = {"bound": "hbm", "kernel": "pack_rows_kernel", "rows_per_launch": n_pack, "kernel_ms": ms_pack,
                 "achieved": bytes_pack / (ms_pack * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": bytes_pack / (ms_pack * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -411,10 +453,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_cpu, cores = cpu_baseline(args.cpu_rows, args.cpu_batch, k)
-        qps_cpu = args.cpu_batch / t_cpu * (args.cpu_rows / n_total)
+        cpu_rows = max(1024, min(args.cpu_rows, int(args.cpu_rows * 1968 / D)))
+        t_cpu, cores = cpu_baseline(cpu_rows, args.cpu_batch, k)
+        qps_cpu = args.cpu_batch / t_cpu * (cpu_rows / n_total)
         cpu = {"value": qps_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_batch} queries x {args.cpu_rows} rows x D={D} fp32 in {t_cpu:.2f} s (numpy/OpenBLAS "
+               "sample": f"{args.cpu_batch} queries x {cpu_rows} rows x D={D} fp32 in {t_cpu:.2f} s (numpy/OpenBLAS "
                          f"sgemm blocks + top-k = faiss IndexFlatIP restated); QPS scaled linearly to {n_total} rows"}
 
     hnsw = None
@@ -424,9 +467,9 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": B / ms_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"combo color+sift+dreamsim (48+128+1792) D={D}, {n_total} rows row-sharded over "
+            "config": {"workload": f"{args.workload_name} D={D}, {n_total} rows row-sharded over "
                                    f"{world} GPU(s) ({n_local} rows/GPU), batch {B}, top-{k}, exact (fp32 re-rank, "
                                    f"certificate)",
                        "l2": "database shard (bf16) per step is far larger than the 126 MB L2; no flush needed",
@@ -438,7 +481,7 @@ def main():
             "extra": {"score_ms": score_ms, "tail_ms": tail_ms, "uncertified_queries": n_unc,
                       "launches_per_step": launches, "exchange": (args.exchange if world > 1 else None), "exchange_matches_nccl": exchange_check,
                       "nccl_path_ms": alt_ms, "build_rows_per_s": n_local / build_s,
-                      "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * 1984) / build_s / 1e9,
+                      "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * Dp) / build_s / 1e9,
                       "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep,
                       "hnsw_baseline": hnsw},
         }

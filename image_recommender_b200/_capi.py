@@ -17,7 +17,7 @@ B2K_LIST = 32
 
 OPT_PATH, OPT_RERANK, OPT_FORCE_EXACT, OPT_SCAN_MAX_B, OPT_SPLITS, OPT_TC_PAIR, OPT_SEED, OPT_TIGHTEN, OPT_COLLECT = 1, 2, 3, 4, 5, 6, 7, 8, 9
 PATH_AUTO, PATH_SCAN, PATH_TC = 0, 1, 2
-E_INVALID, E_CAPACITY, E_IO, E_NODEVICE, E_NOMEM = -1, -2, -3, -4, -5
+E_INVALID, E_CAPACITY, E_IO, E_NODEVICE, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 
 
 class B2KError(RuntimeError):
@@ -52,6 +52,16 @@ SIGNATURES = {
     "b2k_reset": (C.c_int, [C.c_void_p]),
     "b2k_add": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64]),
     "b2k_add_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64, C.c_void_p]),
+    "b2k_stage_open": (C.c_int, [C.c_void_p, C.c_int64]),
+    "b2k_stage_rows": (C.c_int64, [C.c_void_p]),
+    "b2k_stage_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "b2k_stage_wait": (C.c_int, [C.c_void_p, C.c_int32]),
+    "b2k_stage_commit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
+    "b2k_stage_close": (C.c_int, [C.c_void_p]),
+    "b2k_ingest_sqlite": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64,
+                                    C.POINTER(C.c_int64)]),
+    "b2k_parse_f32_blob": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "b2k_table_dims": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "b2k_ntotal": (C.c_int64, [C.c_void_p]),
     "b2k_dim": (C.c_int32, [C.c_void_p]),
     "b2k_dim_padded": (C.c_int32, [C.c_void_p]),

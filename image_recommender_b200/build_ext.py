@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libb2k.so"
-SOURCES = ["api.cu", "pack.cu", "scan.cu", "score_tc.cu", "score_tc2.cu", "select.cu", "xchg.cu"]
+SOURCES = ["api.cu", "pack.cu", "scan.cu", "score_tc.cu", "score_tc2.cu", "select.cu", "xchg.cu", "ingest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     # cudart is linked statically and libcuda is resolved at run time through
     # cudaGetDriverEntryPoint, so the library loads (and exports its symbols) on a GPU-less host.
     cmd = [nvcc, *ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs),
-           "-cudart", "static"]
+           "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -25,7 +25,7 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
-constexpr int64_t kStageRows = 65536;     // rows per staging chunk of add() / load() / fill_synthetic()
+constexpr int64_t kMaxStageRows = 65536;  // rows per staging chunk of add() / load() / fill_synthetic() (fewer for very wide rows)
 constexpr int kMaxNqPerPass = 16384;      // queries per pipeline pass (workspace sizing)
 constexpr int kDefaultCandCap = 0;      // 0: every listed entry can be a candidate (no overflow)
 
@@ -91,6 +91,13 @@ struct b2k_index {
   cudaStream_t stream = nullptr;
   float* stage[B2K_MAX_TABLES] = {nullptr};   // device staging of raw per-table rows
   float* stage_rows_f32 = nullptr;            // device staging of packed rows (load)
+  int64_t stage_rows = kMaxStageRows;         // rows per staging chunk: <= 512 MB of fp32 per chunk
+  // pinned two-slot ingest staging (b2k_stage_*): host rows -> async H2D -> K-pack, overlapped with
+  // the caller filling the other slot
+  float* pin[2][B2K_MAX_TABLES] = {{nullptr}};
+  int64_t pin_rows = 0;
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  bool pin_busy[2] = {false, false};
   Workspace ws;
   // TMA descriptors (host copies; passed by value at launch)
   alignas(64) CUtensorMap tmap_q, tmap_db, tmap_db2;   // tmap_db2: 128-row boxes for the CTA-pair kernel
@@ -115,12 +122,13 @@ int make_col_offsets(b2k_index* ix) {
   for (int t = 0; t < ix->n_tables; ++t) { ix->col_off[t] = off; off += ix->dims[t]; }
   ix->D = off;
   ix->Dp = (off + 63) / 64 * 64;
+  ix->stage_rows = std::max<int64_t>(1024, std::min<int64_t>(kMaxStageRows, ((int64_t)1 << 27) / off));
   return 0;
 }
 
 int ensure_stage(b2k_index* ix) {
   for (int t = 0; t < ix->n_tables; ++t)
-    if (!ix->stage[t]) { int rc = dev_alloc(&ix->stage[t], (size_t)kStageRows * ix->dims[t]); if (rc) return rc; }
+    if (!ix->stage[t]) { int rc = dev_alloc(&ix->stage[t], (size_t)ix->stage_rows * ix->dims[t]); if (rc) return rc; }
   return 0;
 }
 
@@ -424,6 +432,7 @@ void b2k_destroy(b2k_index* ix) {
   dev_free(ix->f32); dev_free(ix->bf16); dev_free(ix->norm2); dev_free(ix->stat_bits);
   for (int t = 0; t < B2K_MAX_TABLES; ++t) dev_free(ix->stage[t]);
   dev_free(ix->stage_rows_f32);
+  b2k_stage_close(ix);
   if (ix->h_fail) cudaFreeHost(ix->h_fail);
   for (int i = 0; i < 3; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
   if (ix->stream) cudaStreamDestroy(ix->stream);
@@ -491,8 +500,8 @@ int b2k_add(b2k_index* ix, const float* const* host_tables, int64_t n) {
   DeviceGuard g(ix->device);
   int rc = ensure_stage(ix);
   if (rc) return rc;
-  for (int64_t r0 = 0; r0 < n; r0 += kStageRows) {
-    const int64_t m = std::min(kStageRows, n - r0);
+  for (int64_t r0 = 0; r0 < n; r0 += ix->stage_rows) {
+    const int64_t m = std::min(ix->stage_rows, n - r0);
     const float* devp[B2K_MAX_TABLES];
     for (int t = 0; t < ix->n_tables; ++t) {
       B2K_CUDA(cudaMemcpyAsync(ix->stage[t], host_tables[t] + r0 * ix->dims[t], (size_t)m * ix->dims[t] * sizeof(float),
@@ -507,8 +516,88 @@ int b2k_add(b2k_index* ix, const float* const* host_tables, int64_t n) {
   return 0;
 }
 
+// ---- pinned two-slot ingest staging --------------------------------------------------------
+int b2k_stage_open(b2k_index* ix, int64_t rows_per_slot) {
+  if (!ix || rows_per_slot < 1) { set_error("stage_open: bad argument"); return B2K_E_INVALID; }
+  DeviceGuard g(ix->device);
+  b2k_stage_close(ix);
+  int rc = ensure_stage(ix);
+  if (rc) return rc;
+  rows_per_slot = std::min(rows_per_slot, ix->stage_rows);
+  for (int s = 0; s < 2; ++s) {
+    for (int t = 0; t < ix->n_tables; ++t)
+      B2K_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ix->pin[s][t]), (size_t)rows_per_slot * ix->dims[t] * sizeof(float)));
+    B2K_CUDA(cudaEventCreateWithFlags(&ix->pin_ev[s], cudaEventDisableTiming));
+    ix->pin_busy[s] = false;
+  }
+  ix->pin_rows = rows_per_slot;
+  return 0;
+}
+
+int64_t b2k_stage_rows(const b2k_index* ix) { return ix ? ix->pin_rows : 0; }
+
+int b2k_stage_ptr(b2k_index* ix, int32_t slot, int32_t table, float** host_ptr) {
+  if (!ix || !host_ptr || slot < 0 || slot > 1 || table < 0 || table >= ix->n_tables || ix->pin_rows == 0) {
+    set_error("stage_ptr: bad argument (stage open?)");
+    return B2K_E_INVALID;
+  }
+  *host_ptr = ix->pin[slot][table];
+  return 0;
+}
+
+int b2k_stage_wait(b2k_index* ix, int32_t slot) {
+  if (!ix || slot < 0 || slot > 1) { set_error("stage_wait: bad argument"); return B2K_E_INVALID; }
+  if (ix->pin_busy[slot]) {
+    DeviceGuard g(ix->device);
+    B2K_CUDA(cudaEventSynchronize(ix->pin_ev[slot]));
+    ix->pin_busy[slot] = false;
+  }
+  return 0;
+}
+
+int b2k_stage_commit(b2k_index* ix, int32_t slot, int64_t n) {
+  if (!ix || slot < 0 || slot > 1 || n < 0 || n > ix->pin_rows) { set_error("stage_commit: bad argument"); return B2K_E_INVALID; }
+  if (ix->ntotal + n > ix->cap) {
+    set_error("stage_commit: %lld + %lld rows exceed the capacity %lld", (long long)ix->ntotal, (long long)n, (long long)ix->cap);
+    return B2K_E_CAPACITY;
+  }
+  if (n == 0) return 0;
+  DeviceGuard g(ix->device);
+  // one device staging set: copy(i+1) is ordered after pack(i) on the same stream; the overlap that
+  // matters is the caller's decode of the other slot against this slot's DMA + pack
+  const float* devp[B2K_MAX_TABLES];
+  for (int t = 0; t < ix->n_tables; ++t) {
+    B2K_CUDA(cudaMemcpyAsync(ix->stage[t], ix->pin[slot][t], (size_t)n * ix->dims[t] * sizeof(float),
+                             cudaMemcpyHostToDevice, ix->stream));
+    devp[t] = ix->stage[t];
+  }
+  int rc = b2k_add_device(ix, devp, n, ix->stream);
+  if (rc) return rc;
+  B2K_CUDA(cudaEventRecord(ix->pin_ev[slot], ix->stream));
+  ix->pin_busy[slot] = true;
+  return 0;
+}
+
+int b2k_stage_close(b2k_index* ix) {
+  if (!ix) return 0;
+  DeviceGuard g(ix->device);
+  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  for (int s = 0; s < 2; ++s) {
+    for (int t = 0; t < B2K_MAX_TABLES; ++t) { if (ix->pin[s][t]) cudaFreeHost(ix->pin[s][t]); ix->pin[s][t] = nullptr; }
+    if (ix->pin_ev[s]) cudaEventDestroy(ix->pin_ev[s]);
+    ix->pin_ev[s] = nullptr; ix->pin_busy[s] = false;
+  }
+  ix->pin_rows = 0;
+  return 0;
+}
+
 int64_t b2k_ntotal(const b2k_index* ix) { return ix ? ix->ntotal : 0; }
 int32_t b2k_dim(const b2k_index* ix) { return ix ? ix->D : 0; }
+int32_t b2k_table_dims(const b2k_index* ix, int32_t* dims_out) {
+  if (!ix) return 0;
+  if (dims_out) for (int t = 0; t < ix->n_tables; ++t) dims_out[t] = ix->dims[t];
+  return ix->n_tables;
+}
 int32_t b2k_dim_padded(const b2k_index* ix) { return ix ? ix->Dp : 0; }
 int64_t b2k_base_offset(const b2k_index* ix) { return ix ? ix->base : 0; }
 
@@ -690,9 +779,9 @@ int b2k_save(b2k_index* ix, const char* path, const int64_t* ids, int64_t n_ids)
   h.rows_offset = sizeof(FileHeader);
   h.ids_offset = h.rows_offset + ix->ntotal * (int64_t)ix->D * 4;
   bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
-  std::vector<float> buf((size_t)std::min<int64_t>(kStageRows, std::max<int64_t>(ix->ntotal, 1)) * ix->D);
-  for (int64_t r0 = 0; ok && r0 < ix->ntotal; r0 += kStageRows) {
-    const int64_t m = std::min(kStageRows, ix->ntotal - r0);
+  std::vector<float> buf((size_t)std::min<int64_t>(ix->stage_rows, std::max<int64_t>(ix->ntotal, 1)) * ix->D);
+  for (int64_t r0 = 0; ok && r0 < ix->ntotal; r0 += ix->stage_rows) {
+    const int64_t m = std::min(ix->stage_rows, ix->ntotal - r0);
     cudaError_t e = cudaMemcpy(buf.data(), ix->f32 + r0 * ix->D, (size_t)m * ix->D * 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { fclose(f); set_error("save: %s", cudaGetErrorString(e)); return (int)e; }
     ok = fwrite(buf.data(), (size_t)ix->D * 4, (size_t)m, f) == (size_t)m;
@@ -747,11 +836,11 @@ int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_en
   if (rc) { fclose(f); return rc; }
   if (ix->D != h.D) { fclose(f); b2k_destroy(ix); set_error("load: corrupt header"); return B2K_E_IO; }
   DeviceGuard g(device);
-  rc = dev_alloc(&ix->stage_rows_f32, (size_t)kStageRows * ix->D);
-  std::vector<float> buf((size_t)std::min<int64_t>(kStageRows, std::max<int64_t>(n, 1)) * ix->D);
+  rc = dev_alloc(&ix->stage_rows_f32, (size_t)ix->stage_rows * ix->D);
+  std::vector<float> buf((size_t)std::min<int64_t>(ix->stage_rows, std::max<int64_t>(n, 1)) * ix->D);
   if (!rc && fseek(f, (long)(h.rows_offset + row_begin * (int64_t)ix->D * 4), SEEK_SET) != 0) { set_error("load: seek failed"); rc = B2K_E_IO; }
-  for (int64_t r0 = 0; !rc && r0 < n; r0 += kStageRows) {
-    const int64_t m = std::min(kStageRows, n - r0);
+  for (int64_t r0 = 0; !rc && r0 < n; r0 += ix->stage_rows) {
+    const int64_t m = std::min(ix->stage_rows, n - r0);
     if (fread(buf.data(), (size_t)ix->D * 4, (size_t)m, f) != (size_t)m) { set_error("load: short read in %s", path); rc = B2K_E_IO; break; }
     cudaError_t e = cudaMemcpyAsync(ix->stage_rows_f32, buf.data(), (size_t)m * ix->D * 4, cudaMemcpyHostToDevice, ix->stream);
     if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; break; }
@@ -794,8 +883,8 @@ int b2k_fill_synthetic(b2k_index* ix, int64_t n, const b2k_synth* p) {
   DeviceGuard g(ix->device);
   int rc = ensure_stage(ix);
   if (rc) return rc;
-  for (int64_t r0 = 0; r0 < n; r0 += kStageRows) {
-    const int64_t m = std::min(kStageRows, n - r0);
+  for (int64_t r0 = 0; r0 < n; r0 += ix->stage_rows) {
+    const int64_t m = std::min(ix->stage_rows, n - r0);
     SynthArgs s;
     fill_synth_args(ix, s, p);
     s.query_mode = 0; s.n = m; s.first = ix->base + ix->ntotal;
@@ -812,8 +901,8 @@ int b2k_fill_synthetic(b2k_index* ix, int64_t n, const b2k_synth* p) {
 
 int b2k_synth_queries_device(b2k_index* ix, int32_t nq, const b2k_synth* p, uint64_t qseed, float sigma_q,
                              float* q_dev, void* stream) {
-  if (!ix || !p || !q_dev || nq < 0 || nq > kStageRows || p->total_rows < 1) {
-    set_error("synth_queries: bad argument (nq <= %lld)", (long long)kStageRows);
+  if (!ix || !p || !q_dev || nq < 0 || nq > ix->stage_rows || p->total_rows < 1) {
+    set_error("synth_queries: bad argument (nq <= %lld)", (long long)(ix ? ix->stage_rows : 0));
     return B2K_E_INVALID;
   }
   DeviceGuard g(ix->device);

@@ -1,0 +1,187 @@
+// Native ingest for the build half of the hot path: SQLite rows -> float32 payloads -> pinned
+// staging -> (async H2D + K-pack).  Replaces the Python row loop of
+//   FAISSIndexBuilderDB._batch_records  (main/create_index.py:144-158: fetchmany over the join)
+//   FAISSIndexBuilderDB._process_batch  (main/create_index.py:160-189: pickle.loads per blob)
+// for databases whose blobs are what the reference's extractors write
+// (vector_scripts/create_vector_base.py:142-145).  Host code only; it drives the engine through
+// the public C ABI (b2k_stage_*), and talks to SQLite through dlopen("libsqlite3.so.0") with the
+// handful of prototypes it needs (the image ships the library but not sqlite3.h).
+#include <dlfcn.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b2k {
+namespace {
+
+// ---- strict recogniser of pickle.dumps(np.ndarray[float32, 1-D, C-contiguous], protocol=5) ----
+// numpy >= 2 reduces such an array to numpy._core.numeric._frombuffer(bytearray, dtype, shape, order):
+//   80 05 | 95 <frame:8> | 8c <len> "numpy._core.numeric" 94 | 8c 0b "_frombuffer" 94 93 94 |
+//   28 (MARK) | 96 <n_bytes:8> <raw little-endian float32> 94 | ... dtype('f4') reduce: 8c 02 "f4" ...
+//   8c 01 "<" ... | shape tuple: (4b d | 4d d:2 | 4a d:4) 85 94 | 8c 01 "C" 94 | 74 94 52 94 2e
+// The checks mirror FAISSIndexBuilderDB._decode_blob's fast path byte for byte (main/create_index.py
+// of this repo), so both decoders accept exactly the same blobs.
+const unsigned char kMark[] = {'_', 'f', 'r', 'o', 'm', 'b', 'u', 'f', 'f', 'e', 'r', 0x94, 0x93, 0x94, 0x28, 0x96};
+const unsigned char kTail[] = {0x8c, 0x01, 'C', 0x94, 0x74, 0x94, 0x52, 0x94, 0x2e};
+const unsigned char kF4[] = {0x8c, 0x02, 'f', '4', 0x94};
+const unsigned char kLE[] = {0x8c, 0x01, '<', 0x94};
+
+const unsigned char* find_bytes(const unsigned char* hay, int64_t n, const unsigned char* needle, int64_t m) {
+  for (int64_t i = 0; i + m <= n; ++i)
+    if (memcmp(hay + i, needle, (size_t)m) == 0) return hay + i;
+  return nullptr;
+}
+
+int parse_blob(const unsigned char* b, int64_t n, const float** payload, int64_t* dim) {
+  if (!b || n < 32 || b[0] != 0x80 || b[1] != 0x05) return B2K_E_UNSUPPORTED;
+  const int64_t head = n < 80 ? n : 80;
+  const unsigned char* m = find_bytes(b, head, kMark, sizeof(kMark));
+  if (!m || m == b) return B2K_E_UNSUPPORTED;
+  const int64_t off = (m - b) + (int64_t)sizeof(kMark) + 8;
+  if (off > n || off > 80) return B2K_E_UNSUPPORTED;      // the length field itself lies in the first 80 bytes
+  uint64_t nb = 0;
+  for (int i = 7; i >= 0; --i) nb = (nb << 8) | b[off - 8 + i];
+  if (nb == 0 || (nb & 3) != 0 || nb > (uint64_t)(n - off)) return B2K_E_UNSUPPORTED;
+  const unsigned char* tail = b + off + nb;
+  const int64_t tl = n - off - (int64_t)nb;
+  if (tl <= 0 || tl >= 160) return B2K_E_UNSUPPORTED;
+  if (!find_bytes(tail, tl, kF4, sizeof(kF4)) || !find_bytes(tail, tl, kLE, sizeof(kLE))) return B2K_E_UNSUPPORTED;
+  const uint64_t d = nb / 4;
+  unsigned char shape[16];
+  int sl = 0;
+  if (d < 256) { shape[sl++] = 'K'; shape[sl++] = (unsigned char)d; }
+  else if (d < 65536) { shape[sl++] = 'M'; shape[sl++] = (unsigned char)(d & 0xff); shape[sl++] = (unsigned char)(d >> 8); }
+  else if (d < 0x80000000ull) { shape[sl++] = 'J'; for (int i = 0; i < 4; ++i) shape[sl++] = (unsigned char)((d >> (8 * i)) & 0xff); }
+  else return B2K_E_UNSUPPORTED;
+  shape[sl++] = 0x85; shape[sl++] = 0x94;
+  memcpy(shape + sl, kTail, sizeof(kTail));
+  sl += (int)sizeof(kTail);
+  if (tl < sl || memcmp(tail + tl - sl, shape, (size_t)sl) != 0) return B2K_E_UNSUPPORTED;
+  *payload = reinterpret_cast<const float*>(b + off);     // unaligned: callers memcpy
+  *dim = (int64_t)d;
+  return 0;
+}
+
+// ---- libsqlite3 through dlopen ---------------------------------------------------------------
+struct Sqlite {
+  void* lib = nullptr;
+  int (*open_v2)(const char*, void**, int, const char*) = nullptr;
+  int (*close)(void*) = nullptr;
+  int (*prepare_v2)(void*, const char*, int, void**, const char**) = nullptr;
+  int (*step)(void*) = nullptr;
+  int (*finalize)(void*) = nullptr;
+  int (*column_count)(void*) = nullptr;
+  int (*column_type)(void*, int) = nullptr;
+  long long (*column_int64)(void*, int) = nullptr;
+  const void* (*column_blob)(void*, int) = nullptr;
+  int (*column_bytes)(void*, int) = nullptr;
+  const char* (*errmsg)(void*) = nullptr;
+  bool load() {
+    if (lib) return true;
+    for (const char* name : {"libsqlite3.so.0", "libsqlite3.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+#define B2K_SYM(field, sym) *reinterpret_cast<void**>(&field) = dlsym(lib, sym); if (!field) return false
+    B2K_SYM(open_v2, "sqlite3_open_v2"); B2K_SYM(close, "sqlite3_close"); B2K_SYM(prepare_v2, "sqlite3_prepare_v2");
+    B2K_SYM(step, "sqlite3_step"); B2K_SYM(finalize, "sqlite3_finalize"); B2K_SYM(column_count, "sqlite3_column_count");
+    B2K_SYM(column_type, "sqlite3_column_type"); B2K_SYM(column_int64, "sqlite3_column_int64");
+    B2K_SYM(column_blob, "sqlite3_column_blob"); B2K_SYM(column_bytes, "sqlite3_column_bytes"); B2K_SYM(errmsg, "sqlite3_errmsg");
+#undef B2K_SYM
+    return true;
+  }
+};
+constexpr int kSqliteOpenReadonly = 1, kSqliteRow = 100, kSqliteDone = 101, kSqliteInteger = 1, kSqliteBlob = 4;
+
+}  // namespace
+}  // namespace b2k
+
+using namespace b2k;
+
+extern "C" {
+
+int b2k_parse_f32_blob(const void* blob, int64_t n_bytes, const float** payload, int64_t* dim) {
+  if (!payload || !dim) { set_error("parse_f32_blob: null output"); return B2K_E_INVALID; }
+  *payload = nullptr; *dim = 0;
+  return parse_blob(static_cast<const unsigned char*>(blob), n_bytes, payload, dim);
+}
+
+int b2k_ingest_sqlite(b2k_index* ix, const char* db_path, const char* sql, int64_t* ids_out, int64_t ids_cap,
+                      int64_t* n_added) {
+  if (!ix || !db_path || !sql || !ids_out || !n_added) { set_error("ingest_sqlite: bad argument"); return B2K_E_INVALID; }
+  *n_added = 0;
+  static Sqlite sq;
+  if (!sq.load()) { set_error("ingest_sqlite: libsqlite3 is not loadable (%s)", dlerror()); return B2K_E_UNSUPPORTED; }
+  int32_t dims[B2K_MAX_TABLES];
+  const int n_tables = b2k_table_dims(ix, dims);
+  if (b2k_stage_rows(ix) == 0) { const int r = b2k_stage_open(ix, 16384); if (r) return r; }
+  const int64_t slot_rows = b2k_stage_rows(ix);
+
+  void* db = nullptr;
+  void* stmt = nullptr;
+  int rc = 0;
+  if (sq.open_v2(db_path, &db, kSqliteOpenReadonly, nullptr) != 0) {
+    set_error("ingest_sqlite: cannot open %s: %s", db_path, db ? sq.errmsg(db) : "out of memory");
+    if (db) sq.close(db);
+    return B2K_E_IO;
+  }
+  if (sq.prepare_v2(db, sql, -1, &stmt, nullptr) != 0) {
+    set_error("ingest_sqlite: %s", sq.errmsg(db));
+    sq.close(db);
+    return B2K_E_IO;
+  }
+  if (sq.column_count(stmt) != 1 + n_tables) {
+    set_error("ingest_sqlite: the query returns %d columns, expected id + %d blobs", sq.column_count(stmt), n_tables);
+    sq.finalize(stmt); sq.close(db);
+    return B2K_E_INVALID;
+  }
+
+  float* dst[B2K_MAX_TABLES];
+  int slot = 0;
+  int64_t in_slot = 0, total = 0;
+  auto bind_slot = [&](int s) -> int {
+    int r = b2k_stage_wait(ix, s);
+    for (int t = 0; t < n_tables && !r; ++t) r = b2k_stage_ptr(ix, s, t, &dst[t]);
+    return r;
+  };
+  rc = bind_slot(slot);
+  while (!rc) {
+    const int st = sq.step(stmt);
+    if (st == kSqliteDone) break;
+    if (st != kSqliteRow) { set_error("ingest_sqlite: %s", sq.errmsg(db)); rc = B2K_E_IO; break; }
+    if (total >= ids_cap) { set_error("ingest_sqlite: more than %lld rows", (long long)ids_cap); rc = B2K_E_CAPACITY; break; }
+    if (sq.column_type(stmt, 0) != kSqliteInteger) { set_error("ingest_sqlite: first column is not an integer id"); rc = B2K_E_UNSUPPORTED; break; }
+    const long long id = sq.column_int64(stmt, 0);
+    for (int t = 0; t < n_tables; ++t) {
+      const float* payload = nullptr;
+      int64_t d = 0;
+      const void* blob = sq.column_type(stmt, 1 + t) == kSqliteBlob ? sq.column_blob(stmt, 1 + t) : nullptr;
+      const int nb = blob ? sq.column_bytes(stmt, 1 + t) : 0;
+      if (parse_blob(static_cast<const unsigned char*>(blob), nb, &payload, &d) != 0 || d != dims[t]) {
+        set_error("ingest_sqlite: image id %lld, table %d: blob is not a pickled 1-D float32 ndarray of %d values",
+                  id, t, dims[t]);
+        rc = B2K_E_UNSUPPORTED;
+        break;
+      }
+      memcpy(dst[t] + in_slot * dims[t], payload, (size_t)d * sizeof(float));
+    }
+    if (rc) break;
+    ids_out[total++] = id;
+    if (++in_slot == slot_rows) {
+      rc = b2k_stage_commit(ix, slot, in_slot);
+      in_slot = 0;
+      slot ^= 1;
+      if (!rc) rc = bind_slot(slot);
+    }
+  }
+  if (!rc && in_slot > 0) rc = b2k_stage_commit(ix, slot, in_slot);
+  sq.finalize(stmt);
+  sq.close(db);
+  // rows committed before a failure stay appended (ids_out[0, *n_added) names them): the caller decides
+  const int rc2 = b2k_stage_wait(ix, 0) | b2k_stage_wait(ix, 1);
+  *n_added = rc ? total - in_slot : total;
+  return rc ? rc : rc2;
+}
+
+}  // extern "C"

@@ -127,6 +127,22 @@ class FlatShard:
         ptrs = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
         check(_lib.b2k_add(self._h, ptrs, n))
 
+    def ingest_sqlite(self, db_path: str, sql: str, max_rows: int, rows_per_slot: int = 16384) -> np.ndarray:
+        """Native build loop (csrc/ingest.cu): run `sql` (id, blob_1..blob_T) through libsqlite3, view
+        the float32 payload of every blob in place, stage rows in pinned memory and K-pack them while
+        the next slot is decoded.  Returns the image ids of the appended rows, in offset order.
+        Raises B2KError(status=E_UNSUPPORTED) on the first blob the strict recogniser does not know
+        (rows committed before it stay appended: reset() and decode in Python instead)."""
+        ids = np.empty((max(int(max_rows), 1),), np.int64)
+        n = C.c_int64(0)
+        check(_lib.b2k_stage_open(self._h, int(rows_per_slot)))
+        try:
+            check(_lib.b2k_ingest_sqlite(self._h, str(db_path).encode(), sql.encode(), ids.ctypes.data,
+                                         int(max_rows), C.byref(n)))
+        finally:
+            _lib.b2k_stage_close(self._h)
+        return ids[:n.value].copy()
+
     def search(self, q, k: int):
         """index.search(query_vec, k) (search_from_image.py:247) -> (distances, labels)."""
         dist, lab, _ = self.search_ip(q, k, want_ip=False)
@@ -226,6 +242,16 @@ class FlatShard:
         return q
 
 
+def parse_f32_blob(blob: bytes):
+    """The strict blob recogniser of the native ingest (host only): float32 vector viewed inside a
+    pickled 1-D ndarray, or None when the blob is in any other format."""
+    ptr, d = C.c_void_p(), C.c_int64(0)
+    if _lib.b2k_parse_f32_blob(blob, len(blob), C.byref(ptr), C.byref(d)) != 0:
+        return None
+    off = ptr.value - C.cast(C.c_char_p(blob), C.c_void_p).value
+    return np.frombuffer(blob, dtype="<f4", count=d.value, offset=off)
+
+
 def file_info(path: str) -> dict:
     n = C.c_int64(0)
     nt = C.c_int32(0)
@@ -260,4 +286,4 @@ def merge_topk_device(ip, dist, labels, out=None, stream=None):
 
 
 __all__ = ["FlatShard", "B2KError", "normalize_L2", "device_count", "file_info", "load_ids",
-           "merge_topk_device"]
+           "merge_topk_device", "parse_f32_blob"]

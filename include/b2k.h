@@ -33,6 +33,7 @@ extern "C" {
 #define B2K_E_IO       (-3)   /* save/load failure                              */
 #define B2K_E_NODEVICE (-4)   /* no CUDA device / wrong architecture            */
 #define B2K_E_NOMEM    (-5)   /* host allocation failure                        */
+#define B2K_E_UNSUPPORTED (-6) /* input format this fast path does not handle    */
 
 typedef struct b2k_index b2k_index;
 
@@ -99,9 +100,37 @@ int b2k_add(b2k_index* idx, const float* const* host_tables, int64_t n);
 /* Same with device-resident inputs on `stream` (cudaStream_t as void*). */
 int b2k_add_device(b2k_index* idx, const float* const* dev_tables, int64_t n, void* stream);
 
+/* Pinned two-slot ingest staging: the zero-copy form of add() for a host-side decoder
+ * (replaces the np.stack(...).astype("float32") batch materialisation of
+ * main/create_index.py:288,310 together with index.add, :311).  The caller writes decoded rows of
+ * table t straight into slot s's pinned buffer ([rows_per_slot, d_t] fp32, b2k_stage_ptr), commits
+ * the slot (asynchronous H2D + K-pack, appends n rows) and fills the other slot meanwhile;
+ * b2k_stage_wait(s) blocks until slot s may be overwritten again.  close() drains and frees. */
+int     b2k_stage_open(b2k_index* idx, int64_t rows_per_slot);
+int64_t b2k_stage_rows(const b2k_index* idx);      /* rows per slot actually allocated (0 = closed) */
+int     b2k_stage_ptr(b2k_index* idx, int32_t slot, int32_t table, float** host_ptr);
+int     b2k_stage_wait(b2k_index* idx, int32_t slot);
+int     b2k_stage_commit(b2k_index* idx, int32_t slot, int64_t n_rows);
+int     b2k_stage_close(b2k_index* idx);
+
+/* Native ingest: replaces the Python row loop of FAISSIndexBuilderDB._batch_records +
+ * _process_batch (main/create_index.py:144-189) for databases whose vector blobs are what the
+ * reference's extractors write (vector_scripts/create_vector_base.py:142-145:
+ * pickle.dumps(1-D float32 ndarray, HIGHEST_PROTOCOL) under numpy >= 2).  Runs `sql` (first column
+ * = images.id, then one blob column per table, in the index's table order) through libsqlite3,
+ * views each blob's float32 payload in place, writes it into the pinned staging slots and commits
+ * them as they fill.  ids_out[i] = image id of the i-th appended row.  Any blob in another format
+ * (or of another length) stops the call with B2K_E_UNSUPPORTED *before* that row is staged:
+ * the caller resets the index and falls back to its own decoder (the reference's pickle.loads).
+ * b2k_parse_f32_blob is the strict recogniser it uses (host only; 0 = recognised). */
+int b2k_ingest_sqlite(b2k_index* idx, const char* db_path, const char* sql, int64_t* ids_out,
+                      int64_t ids_cap, int64_t* n_added);
+int b2k_parse_f32_blob(const void* blob, int64_t n_bytes, const float** payload, int64_t* dim);
+
 /* index.ntotal (main/create_index.py:321, main/search_from_image.py:340) */
 int64_t b2k_ntotal(const b2k_index* idx);
 int32_t b2k_dim(const b2k_index* idx);
+int32_t b2k_table_dims(const b2k_index* idx, int32_t* dims_out);   /* returns n_tables; dims_out may be NULL */
 int32_t b2k_dim_padded(const b2k_index* idx);
 int64_t b2k_base_offset(const b2k_index* idx);
 

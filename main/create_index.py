@@ -40,6 +40,7 @@ class FAISSIndexBuilderDB:
         log_file: str = "faiss_builder.log",
         log_dir: str = "logs",
         device: int = 0,
+        native_ingest: bool = True,
     ):
         # reference: create_index.py:14-53 (same attribute names; `device` is new)
         self.log_dir = log_dir
@@ -61,6 +62,7 @@ class FAISSIndexBuilderDB:
         self.efConstruction = efConstruction
         self.efSearch = efSearch
         self.device = device
+        self.native_ingest = native_ingest     # new: SQL -> decode -> pack loop in libb2k.so (csrc/ingest.cu)
 
         self.offset_table = f"faiss_index_offsets_{name}"
 
@@ -210,6 +212,32 @@ class FAISSIndexBuilderDB:
         )
         return index
 
+    def _build_native(self, total):
+        """Fresh builds: the whole SQL -> decode -> stage -> pack loop runs in libb2k.so
+        (b2k_ingest_sqlite).  The table dims come from the first row, decoded here.  Returns
+        (index, ids), or (None, []) when some blob is not in the extractors' format — the Python
+        decoder below then rebuilds from scratch (pickle.loads semantics, row skipping included)."""
+        from image_recommender_b200 import B2KError, _capi
+        select_cols, join_strs = self._make_select_and_joins()
+        sql = f"SELECT {select_cols} FROM images i {join_strs}"
+        first = self.read_cur.execute(sql + " LIMIT 1").fetchone()
+        if first is None:
+            return None, []
+        try:
+            dims = [int(self._decode_blob(b).shape[0]) for b in first[1:]]
+        except Exception:
+            return None, []
+        index = self._initialize_index(dims, total)
+        try:
+            ids = index.ingest_sqlite(self.db_path, sql, total)
+        except B2KError as e:
+            index.close()
+            if e.status != _capi.E_UNSUPPORTED:
+                raise
+            self._log(f"Native ingest declined ({e}); decoding in Python.", level="warning")
+            return None, []
+        return index, [int(i) for i in ids]
+
     def _store_offsets(self, ids, start_offset):
         pairs = [(rid, start_offset + i) for i, rid in enumerate(ids)]
         self.write_cur.executemany(
@@ -257,7 +285,15 @@ class FAISSIndexBuilderDB:
             return
 
         batch_num = 0
-        for batch in self._batch_records():
+        native_done = False
+        if index is None and self.native_ingest:
+            index, ids = self._build_native(total)
+            if index is not None:
+                for lo in range(0, len(ids), self.batch_size):
+                    self._store_offsets(ids[lo:lo + self.batch_size], lo)
+                all_ids, offset_counter, native_done = ids, len(ids), True
+                self._log(f"Native ingest: added {offset_counter} vectors.", level="info")
+        for batch in (() if native_done else self._batch_records()):
             batch_num += 1
             ids, parts = self._decode_batch(batch)
             if known:

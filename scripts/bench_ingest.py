@@ -1,0 +1,46 @@
+"""GPU box: build-half throughput, native ingest (csrc/ingest.cu) vs the Python decode loop, on a
+synthetic SQLite DB in the reference's schema and blob format.  Usage: python scripts/bench_ingest.py [rows]"""
+import json, sys, time, tempfile, shutil
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tests"))
+import numpy as np
+from test_ingest import _make_db
+from main.create_index import FAISSIndexBuilderDB
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
+tmp = Path(tempfile.mkdtemp(prefix="b2k_ingest_"))
+t0 = time.perf_counter(); _make_db(tmp / "images.db", n, seed=5); t_db = time.perf_counter() - t0
+res = {"rows": n, "db_mb": round((tmp / "images.db").stat().st_size / 1e6, 1), "make_db_s": round(t_db, 2)}
+files = {}
+for name, native in (("warmup", True), ("native", True), ("python", False)):
+    out = tmp / f"{name}.faiss"
+    b = FAISSIndexBuilderDB(db_path=str(tmp / "images.db"), vector_types=["color", "sift", "dreamsim"], index_file=str(out),
+                            log_dir=str(tmp / "logs"), native_ingest=native)
+    b._log = lambda m, level="info": None
+    t0 = time.perf_counter(); b.build_index(); dt = time.perf_counter() - t0
+    res[name] = {"s": round(dt, 3), "rows_per_s": round(n / dt)}
+    files[name] = out
+# the ingest loops alone (no COUNT(*), offset table, index file)
+import image_recommender_b200 as irb
+b = FAISSIndexBuilderDB(db_path=str(tmp / "images.db"), vector_types=["color", "sift", "dreamsim"], log_dir=str(tmp / "logs"))
+b._log = lambda m, level="info": None
+sel, joins = b._make_select_and_joins()
+sql = f"SELECT {sel} FROM images i {joins}"
+for rep in range(2):
+    ix = irb.FlatShard([48, 128, 1792], n, device=0)
+    t0 = time.perf_counter(); ids = ix.ingest_sqlite(tmp / "images.db", sql, n); dt = time.perf_counter() - t0
+    assert len(ids) == n
+    res["native_loop"] = {"s": round(dt, 3), "rows_per_s": round(n / dt), "gb_per_s": round(n * 7872 / dt / 1e9, 2)}
+    ix.close()
+    ix = irb.FlatShard([48, 128, 1792], n, device=0)
+    t0 = time.perf_counter()
+    for batch in b._batch_records():
+        ids_b, parts = b._decode_batch(batch)
+        ix.add_tables([np.stack([p[t] for p in parts]).astype("float32") for t in range(3)])
+    dt = time.perf_counter() - t0
+    res["python_loop"] = {"s": round(dt, 3), "rows_per_s": round(n / dt)}
+    ix.close()
+res["identical_files"] = files["native"].read_bytes() == files["python"].read_bytes()
+print(json.dumps(res))
+shutil.rmtree(tmp, ignore_errors=True)

@@ -295,6 +295,25 @@ def test_near_duplicate_runs_are_collected(gpu, path):
     ix.close()
 
 
+@pytest.mark.parametrize("dims,n", [([32768], 700), ([4096, 64], 1500), ([128], 5000)])
+def test_other_baseline_dims_match_oracle(gpu, dims, n):
+    """BASELINE configs 4 / 4s: the raw 32768-d SIFT-VLAD descriptor (wider than K-scan's register
+    budget: every batch size takes the tcgen05 path), a wide two-table combo, and the stored 128-d
+    table.  Pack, batch-1 and batch-130 search bit-equal to the oracle."""
+    irb = _irb()
+    tabs, pk = _mk(n, dims)
+    ix = irb.FlatShard(dims, n, device=gpu)
+    ix.add_tables(tabs)
+    f, b, n2 = ix.get_rows(0, n)
+    assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32)) and np.array_equal(b, pk["bf16"])
+    q = oracle.synth_queries(dims, 130, n, n_clusters=8, qseed=77)
+    st1 = _check(ix, pk, q[:1], 10)
+    assert st1["path"] == (1 if sum(dims) <= 4096 else 2)
+    st = _check(ix, pk, q, 10)
+    assert st["path"] == 3 and st["n_uncertified"] == 0
+    ix.close()
+
+
 def test_base_offset_and_two_shard_merge(gpu):
     import torch
     irb = _irb()
