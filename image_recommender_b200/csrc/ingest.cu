@@ -115,7 +115,7 @@ int b2k_ingest_sqlite(b2k_index* ix, const char* db_path, const char* sql, int64
   if (!sq.load()) { set_error("ingest_sqlite: libsqlite3 is not loadable (%s)", dlerror()); return B2K_E_UNSUPPORTED; }
   int32_t dims[B2K_MAX_TABLES];
   const int n_tables = b2k_table_dims(ix, dims);
-  if (b2k_stage_rows(ix) == 0) { const int r = b2k_stage_open(ix, 16384); if (r) return r; }
+  if (b2k_stage_rows(ix) == 0) { const int r = b2k_stage_open(ix, 4096); if (r) return r; }
   const int64_t slot_rows = b2k_stage_rows(ix);
 
   void* db = nullptr;

@@ -127,7 +127,7 @@ class FlatShard:
         ptrs = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
         check(_lib.b2k_add(self._h, ptrs, n))
 
-    def ingest_sqlite(self, db_path: str, sql: str, max_rows: int, rows_per_slot: int = 16384) -> np.ndarray:
+    def ingest_sqlite(self, db_path: str, sql: str, max_rows: int, rows_per_slot: int = 4096) -> np.ndarray:
         """Native build loop (csrc/ingest.cu): run `sql` (id, blob_1..blob_T) through libsqlite3, view
         the float32 payload of every blob in place, stage rows in pinned memory and K-pack them while
         the next slot is decoded.  Returns the image ids of the appended rows, in offset order.

@@ -27,7 +27,7 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
-from image_recommender_b200 import FlatShard, normalize_L2  # noqa: E402
+from image_recommender_b200 import FlatShard, file_info, load_ids, normalize_L2, parse_f32_blob  # noqa: E402
 
 VALID_TYPES = ["color", "hog", "lpips", "dreamsim", "sift", "color_sift", "sift_dreamsim"]
 TABLES = {  # type -> (table, column)   (create_db.py:59-85)
@@ -66,6 +66,7 @@ class ImageRecommender:
         self.top_k = top_k
         self.index_dir = Path(index_dir)
         self._resident = {}      # index file -> (mtime, FlatShard)
+        self._resident_ids = {}  # id(FlatShard) -> image id per offset (from the index file), when stored
         logging.basicConfig(level=logging.INFO, format="%(asctime)s [%(levelname)s] %(message)s")
 
     # ---- query-vector acquisition (search_from_image.py:50-216) -------------------------------
@@ -85,7 +86,15 @@ class ImageRecommender:
             conn.close()
         if not vrow or vrow[0] is None:
             return None
-        blob = vrow[0]
+        return self._decode_cached_blob(vrow[0], vector_column, path_rel)
+
+    @staticmethod
+    def _decode_cached_blob(blob, vector_column="", path_rel=""):
+        """Blob -> [1, d] array with the reference's rules (search_from_image.py:70-91): unpickle
+        (tensors moved to numpy), else raw little-endian float32."""
+        fast = parse_f32_blob(blob) if isinstance(blob, bytes) else None
+        if fast is not None:          # pickled 1-D float32 ndarray: the same floats, without the unpickler
+            return fast.reshape(1, -1)
         try:
             arr = pickle.loads(blob)
             if hasattr(arr, "cpu"):
@@ -144,19 +153,130 @@ class ImageRecommender:
         return results
 
     def search_batch(self, query_groups, index_type: str = "color"):
-        """New: one query vector per group of image paths, searched as one batch."""
+        """New: one query vector per group of image paths, all groups searched as ONE
+        batch.  Same arithmetic as `search_similar_images` per group (concat -> mean over the group's
+        images -> whole-vector normalise -> exact top-k -> offset -> path), but the SQLite work is
+        batched: cached vectors are fetched with `IN (...)` selects on one connection instead of
+        three selects per image, and hits are mapped through the id column kept in the index file
+        instead of two selects per hit.  Returns one result list per group (None for a group
+        without any usable image)."""
         ordered = self._get_ordered_index_types(index_type)
         if not ordered:
             return None
         index, offset_table, file_order = self._load_faiss_index("_".join(ordered), ordered)
         if index is None:
             return None
-        vecs = [self._extract_query_vector([self._relative(p) for p in g], file_order) for g in query_groups]
-        if any(v is None for v in vecs):
-            return None
-        q = np.ascontiguousarray(np.concatenate(vecs, axis=0), dtype=np.float32)
+        groups_rel = [[self._relative(p) for p in g] for g in query_groups]
+        q, live = self._extract_query_matrix(groups_rel, file_order)
+        out = [None] * len(groups_rel)
+        if q is None:
+            return out
         distances, indices = index.search(q, self.top_k)
-        return [self._fetch_results(indices[i:i + 1], distances[i:i + 1], offset_table) for i in range(len(vecs))]
+        for row, res in zip(live, self._fetch_results_batch(indices, distances, offset_table, index)):
+            out[row] = res or None
+        return out
+
+    # ---- batched SQLite access (new) --------------------------------------------------------------
+    _SQL_CHUNK = 900        # bound variables per statement (SQLite's historical limit is 999)
+
+    def _select_in(self, cur, sql_fmt: str, keys):
+        """Runs sql_fmt.format(marks=...) over `keys` in chunks; yields rows."""
+        keys = list(keys)
+        for lo in range(0, len(keys), self._SQL_CHUNK):
+            part = keys[lo:lo + self._SQL_CHUNK]
+            yield from cur.execute(sql_fmt.format(marks=",".join("?" * len(part))), part)
+
+    def _fetch_vectors_batch(self, paths_rel, ordered):
+        """{path_rel: [1, D] float32 concat of the cached parts in `ordered`} for every path whose
+        parts are all cached (the per-image rules of _get_db_vector / _extract_query_vector)."""
+        uniq = list(dict.fromkeys(paths_rel))
+        prefixed = {p: f"{self.images_root.name}/{p}" for p in uniq}
+        conn = sqlite3.connect(self.db_path)
+        try:
+            cur = conn.cursor()
+            by_path = dict((path, i) for i, path in self._select_in(
+                cur, "SELECT id, path FROM images WHERE path IN ({marks})", list(uniq) + list(prefixed.values())))
+            ids = {p: by_path.get(p, by_path.get(prefixed[p])) for p in uniq}      # exact path first (reference order)
+            want = sorted({i for i in ids.values() if i is not None})
+            blobs = {}
+            for t in ordered:
+                table, col = TABLES[t]
+                blobs[t] = dict(self._select_in(cur, f"SELECT image_id, {col} FROM {table} WHERE image_id IN ({{marks}})", want))
+        finally:
+            conn.close()
+        out = {}
+        for p in uniq:
+            parts = []
+            for t in ordered:
+                blob = blobs[t].get(ids[p]) if ids[p] is not None else None
+                v = self._decode_cached_blob(blob, TABLES[t][1], p) if blob is not None else None
+                if v is None:
+                    logging.error(f"No cached {TABLES[t][1]} for '{p}' (feature extraction is out of scope here: "
+                                  f"run the reference's vector_scripts first).")
+                    parts = None
+                    break
+                parts.append(v.reshape(1, -1) if v.ndim == 1 else v)
+            if parts is None:
+                logging.error(f"Could not load all vector features for '{p}', skipping this image.")
+                continue
+            out[p] = np.concatenate(parts, axis=1).astype("float32")
+        return out
+
+    def _extract_query_matrix(self, groups_rel, ordered):
+        """([G', D] normalised query matrix, indices of the groups it holds) — row g is bit-identical
+        to _extract_query_vector(groups_rel[g], ordered)."""
+        if any(t not in TABLES for t in ordered):
+            logging.error(f"Unknown vector type in {ordered}.")
+            return None, []
+        vecs = self._fetch_vectors_batch([p for g in groups_rel for p in g], ordered)
+        rows, live = [], []
+        for gi, g in enumerate(groups_rel):
+            have = [vecs[p] for p in g if p in vecs]
+            if not have:
+                logging.error("Could not extract a vector for any of the query images.")
+                continue
+            rows.append(np.mean(have, axis=0))
+            live.append(gi)
+        if not rows:
+            return None, []
+        q = np.ascontiguousarray(np.concatenate(rows, axis=0), dtype=np.float32)
+        normalize_L2(q, device=self.device)
+        return q, live
+
+    def _fetch_results_batch(self, indices, distances, offset_table, index=None):
+        """Per query row: [(path, distance)] ascending, as _fetch_results; offsets -> image ids through
+        the id column of the index file when it has one (else one IN-select on the offset table),
+        ids -> paths with one IN-select per chunk."""
+        offs = sorted({int(o) for o in np.asarray(indices).ravel() if o >= 0})
+        ids_resident = self._resident_ids.get(id(index)) if index is not None else None
+        conn = sqlite3.connect(self.db_path)
+        try:
+            cur = conn.cursor()
+            if ids_resident is not None:
+                off2id = {o: int(ids_resident[o]) for o in offs if o < len(ids_resident)}
+            else:
+                off2id = dict(self._select_in(cur, f"SELECT offset, image_id FROM {offset_table} WHERE offset IN ({{marks}})", offs))
+            id2path = dict(self._select_in(cur, "SELECT id, path FROM images WHERE id IN ({marks})", sorted(set(off2id.values()))))
+        finally:
+            conn.close()
+        out = []
+        for qi in range(len(indices)):
+            res = []
+            for rank, offset in enumerate(indices[qi]):
+                if offset < 0:
+                    continue
+                image_id = off2id.get(int(offset))
+                if image_id is None:
+                    logging.warning(f"No entry found for offset={offset} in {offset_table}")
+                    continue
+                path = id2path.get(image_id)
+                if path is None:
+                    logging.warning(f"No path found for id={image_id}")
+                    continue
+                res.append((Path(self.base_dir) / path, float(distances[qi, rank])))
+            res.sort(key=lambda x: x[1])
+            out.append(res)
+        return out
 
     def _relative(self, p):
         # search_from_image.py:230-232
@@ -218,8 +338,13 @@ class ImageRecommender:
                 hit = self._resident.get(str(f))
                 if hit is None or hit[0] != mtime:
                     if hit is not None:
+                        self._resident_ids.pop(id(hit[1]), None)
                         hit[1].close()
-                    self._resident[str(f)] = (mtime, FlatShard.load(f, device=self.device))
+                    shard = FlatShard.load(f, device=self.device)
+                    self._resident[str(f)] = (mtime, shard)
+                    info = file_info(f)
+                    if info["has_ids"]:
+                        self._resident_ids[id(shard)] = load_ids(f, 0, info["n_rows"])
                     logging.info(f"Loaded index '{f}' with {self._resident[str(f)][1].ntotal} vectors.")
                 return self._resident[str(f)][1], f"faiss_index_offsets_{name}", list(order)
             except Exception as e:
@@ -277,6 +402,7 @@ class ImageRecommender:
         for _, ix in self._resident.values():
             ix.close()
         self._resident.clear()
+        self._resident_ids.clear()
 
 
 def main(argv=None):

@@ -29,9 +29,17 @@ sel, joins = b._make_select_and_joins()
 sql = f"SELECT {sel} FROM images i {joins}"
 for rep in range(2):
     ix = irb.FlatShard([48, 128, 1792], n, device=0)
-    t0 = time.perf_counter(); ids = ix.ingest_sqlite(tmp / "images.db", sql, n); dt = time.perf_counter() - t0
-    assert len(ids) == n
-    res["native_loop"] = {"s": round(dt, 3), "rows_per_s": round(n / dt), "gb_per_s": round(n * 7872 / dt / 1e9, 2)}
+    from image_recommender_b200.index import _lib, check
+    import ctypes as C
+    t0 = time.perf_counter(); check(_lib.b2k_stage_open(ix._h, 4096)); t_open = time.perf_counter() - t0
+    ids = np.empty(n, np.int64); cnt = C.c_int64(0)
+    t0 = time.perf_counter()
+    check(_lib.b2k_ingest_sqlite(ix._h, str(tmp / "images.db").encode(), sql.encode(), ids.ctypes.data, n, C.byref(cnt)))
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); _lib.b2k_stage_close(ix._h); t_close = time.perf_counter() - t0
+    assert cnt.value == n
+    res["native_loop"] = {"s": round(dt, 3), "rows_per_s": round(n / dt), "gb_per_s": round(n * 7872 / dt / 1e9, 2),
+                          "stage_open_s": round(t_open, 3), "stage_close_s": round(t_close, 3)}
     ix.close()
     ix = irb.FlatShard([48, 128, 1792], n, device=0)
     t0 = time.perf_counter()

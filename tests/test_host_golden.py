@@ -129,6 +129,45 @@ def test_fetch_results_match_reference(workdir):
     assert len(res) == 1
 
 
+def test_batched_query_acquisition_equals_per_image_path(workdir, monkeypatch):
+    """search_batch's IN-select acquisition builds, per group, the same bits as the
+    reference-shaped per-image path (_extract_query_vector), and maps hits like _fetch_results."""
+    import main.search_from_image as sfi
+    monkeypatch.setattr(sfi, "normalize_L2", lambda x, device=0: None)      # compare what is handed to it
+    rec = sfi.ImageRecommender(images_root="image_data", db_path="images.db")
+    conn = sqlite3.connect("images.db")
+    paths = [p for (p,) in conn.execute("SELECT path FROM images ORDER BY id")]
+    conn.close()
+    ordered = ["color", "dreamsim", "sift"]
+    i2, i5 = "image_data/set/img_0002.jpg", "image_data/set/img_0005.jpg"      # the golden q1 / q2 images
+    groups = [[i2], [i2, i5], ["set/" + Path(paths[8]).name], [paths[0], "image_data/set/missing.jpg"],
+              ["image_data/set/missing.jpg"], [paths[3], paths[3], paths[9]]]
+    q, live = rec._extract_query_matrix(groups, ordered)
+    want = [rec._extract_query_vector(g, ordered) for g in groups]
+    assert live == [i for i, w in enumerate(want) if w is not None] and 4 not in live
+    for row, gi in enumerate(live):
+        assert np.array_equal(q[row:row + 1].view(np.uint32), want[gi].view(np.uint32))
+    assert np.array_equal(q[0:1].view(np.uint32), G["q1/combined"].view(np.uint32))
+    assert np.array_equal(q[1:2].view(np.uint32), G["q2/combined"].view(np.uint32))
+    # hits -> paths: through the offset table, and through ids kept with the index
+    b = _builder(["color", "sift", "dreamsim"])
+    off, all_ids = 0, []
+    for batch in b._batch_records():
+        i, _ = b._process_batch(batch)
+        b._store_offsets(i, off)
+        off += len(i)
+        all_ids += i
+    idx = np.array([[3, 0, 10, 7], [5, -1, 2, 2], [23, 22, 21, 20]])
+    dist = np.array([[0.5, 0.25, 0.75, 0.125], [0.1, 3.4e38, 0.3, 0.2], [4, 3, 2, 1]], dtype=np.float32)
+    table = "faiss_index_offsets_color_sift_dreamsim"
+    single = [rec._fetch_results(idx[i:i + 1], dist[i:i + 1], table) for i in range(3)]
+    assert rec._fetch_results_batch(idx, dist, table) == single
+    token = object()
+    rec._resident_ids[id(token)] = np.asarray(all_ids, dtype=np.int64)
+    assert rec._fetch_results_batch(idx, dist, table, token) == single
+    assert [str(p.relative_to(rec.base_dir)) for p, _ in single[0]] == G["fetch/paths"].tolist()
+
+
 def test_cli_parsers():
     import main.create_index as ci
     import main.search_from_image as sfi

@@ -138,3 +138,30 @@ def test_hnsw_restatement_recall():
     assert rec[64] >= 0.95 and rec[64] >= rec[10] - 1e-9
     same = l == lab
     assert np.allclose(d[same], dist[same], atol=1e-4)      # METRIC_L2 values, as index.search returns
+
+
+def test_oracle_agrees_with_third_party_exact_knn():
+    """Independent implementations of the same exact search (scikit-learn brute-force kNN on the
+    squared-L2 metric the reference's index uses, scipy cdist in fp64): the oracle's ids are theirs
+    wherever the fp64 gap between consecutive neighbours exceeds fp32 resolution."""
+    from scipy.spatial.distance import cdist
+    from sklearn.neighbors import NearestNeighbors
+    n, nq, k = 4000, 25, 10
+    pk = oracle.pack(oracle.synth_rows(DIMS, n, n_clusters=4))
+    q = oracle.synth_queries(DIMS, nq, n, n_clusters=4)
+    dist, lab, ip = oracle.search_exact(pk["f32"], q, k, pk["norm2"])
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="sqeuclidean").fit(pk["f32"].astype(np.float64))
+    d_sk, i_sk = nn.kneighbors(q.astype(np.float64))
+    d64 = cdist(q.astype(np.float64), pk["f32"].astype(np.float64), "sqeuclidean")
+    checked = 0
+    for r in range(nq):
+        order = np.argsort(d64[r], kind="stable")[:k + 1]
+        gaps = np.diff(d64[r][order])
+        clear = gaps > 1e-5                      # neighbours separated by more than fp32 rounding
+        for j in range(k):
+            if clear[j] and (j == 0 or clear[j - 1]):
+                assert lab[r, j] == order[j] == i_sk[r, j]
+                checked += 1
+        assert np.allclose(dist[r], d64[r][lab[r]], atol=2e-5)
+        assert np.allclose(d_sk[r], d64[r][i_sk[r]], atol=1e-9)
+    assert checked > 0.8 * nq * k
