@@ -108,7 +108,7 @@ struct b2k_index {
   int opt_tighten = 1;                        // exact-score tightening of the candidate threshold
   int opt_collect = 1;                        // K-collect serves saturated lists (else: exhaustive scan)
   // options
-  int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 1, opt_splits = 0;
+  int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 0, opt_splits = 0;
   b2k_stats stats;
   int32_t* h_fail = nullptr;                  // pinned
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // before scoring, after scoring, after the tail
@@ -242,7 +242,9 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // the fused selection stops being the epilogue's bottleneck (DESIGN.md "seeding").
     const int64_t tiles_total = (ix->ntotal + 255) / 256;
     const int64_t tiles_per_split = tiles_total / ta.plan.n_splits;
-    const bool seed = ix->opt_seed && tiles_per_split >= 16;
+    // tiny batches on short splits: one launch without a floor beats sampling + seeding + main pass
+    // (a single live query per warp inserts without divergence; gpurun_out/exp_path.log)
+    const bool seed = ix->opt_seed && tiles_per_split >= 16 && (ix->opt_seed > 1 || nq > 4 || tiles_per_split >= 128);
     // sample ~0.75 % of the shard whatever the split count: a smaller sample leaves the floor too low
     // (more list insertions in the main pass), a larger one costs more than it saves
     int sample_tiles = ix->opt_seed > 1 ? ix->opt_seed : (int)((tiles_per_split * 3 + 200) / 400);

@@ -130,3 +130,72 @@ class ShardedSearcher:
         g_dist = g_fl[:, 0].contiguous()
         g_ip = g_fl[:, 1].contiguous()
         return self.merge(g_ip, g_dist, g_lab)
+
+
+class ShardedIndex:
+    """faiss index protocol (`search`, `ntotal`, `d`) over a row-sharded index file: every rank of
+    the process group loads ITS row range of the file (b2k_load's range form), searches it locally
+    and exchanges the per-shard top-k (K-exchange over NVLink peer memory, or NCCL all-gather +
+    K-merge).  SPMD: every rank calls `search` with the same queries and gets the same global
+    result — ids are the file's global offsets, exactly what a single-GPU load returns."""
+
+    def __init__(self, shard, n_total: int, group=None, exchange: "PeerExchange | None" = None):
+        from .index import merge_topk_device
+        self.shard = shard
+        self.n_total = int(n_total)
+        self.exchange = exchange
+        self._searcher = ShardedSearcher(lambda q, k, out: shard.search_device(q, k, out=out),
+                                         lambda ip, d, l: merge_topk_device(ip, d, l),
+                                         group=group, exchange=exchange)
+
+    @classmethod
+    def load(cls, path, device: int, group=None, peer: bool = True, max_batch: int = 4096) -> "ShardedIndex":
+        import torch.distributed as dist
+        from .index import FlatShard, file_info
+        info = file_info(path)
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        r0, r1 = shard_range(info["n_rows"], world, rank)
+        shard = FlatShard.load(path, device=device, row_begin=r0, row_end=r1)
+        exchange = None
+        if world > 1 and peer:
+            from ._capi import B2K_MAX_K
+            exchange = PeerExchange(device, rank, world, max_entries=max_batch * B2K_MAX_K, group=group)
+        out = cls(shard, info["n_rows"], group=group, exchange=exchange)
+        out._max_batch = max_batch
+        return out
+
+    @property
+    def ntotal(self) -> int:
+        return self.n_total
+
+    @property
+    def d(self) -> int:
+        return self.shard.d
+
+    is_trained = True
+
+    def search(self, q, k: int):
+        """q: float32 [nq, D] host array, identical on every rank -> (distances [nq,k], labels [nq,k])."""
+        import numpy as np
+        import torch
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        dev = torch.device("cuda", self.shard.device)
+        dist_out = np.empty((q.shape[0], k), np.float32)
+        lab_out = np.empty((q.shape[0], k), np.int64)
+        step = getattr(self, "_max_batch", 4096)
+        with torch.cuda.device(dev):
+            for lo in range(0, q.shape[0], step):
+                qd = torch.from_numpy(q[lo:lo + step]).to(dev)
+                d_, l_, _ = self._searcher.search_device(qd, k)
+                dist_out[lo:lo + step] = d_.cpu().numpy()
+                lab_out[lo:lo + step] = l_.cpu().numpy()
+        return dist_out, lab_out
+
+    def close(self) -> None:
+        if self.exchange is not None:
+            self.exchange.close()
+            self.exchange = None
+        self.shard.close()

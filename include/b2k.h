@@ -42,7 +42,8 @@ typedef struct b2k_index b2k_index;
 #define B2K_OPT_RERANK        2  /* re-rank candidate slots per query: 0 = every listed entry (default),  */
                                  /* else 32..8192 (overflowing queries take the exact fp32 scan)          */
 #define B2K_OPT_FORCE_EXACT   3  /* 1 = treat every query as uncertified (exercise the exact fp32 scan) */
-#define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 1)    */
+#define B2K_OPT_SCAN_MAX_B    4  /* auto path: nq <= this uses K-scan, above uses K-score (default 0: the  */
+                                 /* tcgen05 path measured faster at every batch size and row width)      */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
 #define B2K_OPT_TIGHTEN       8  /* candidate threshold from the exact scores of the k best rows: 1 on (default) */
 #define B2K_OPT_COLLECT       9  /* saturated partial lists are re-scanned by K-collect: 1 on (default), 0 = exhaustive scan */

@@ -340,7 +340,7 @@ class ImageRecommender:
                     if hit is not None:
                         self._resident_ids.pop(id(hit[1]), None)
                         hit[1].close()
-                    shard = FlatShard.load(f, device=self.device)
+                    shard = self._load_index_file(f)
                     self._resident[str(f)] = (mtime, shard)
                     info = file_info(f)
                     if info["has_ids"]:
@@ -352,6 +352,20 @@ class ImageRecommender:
                 return None, None, None
         logging.error(f"Error loading index 'index_hnsw_{canonical}.faiss': no such file in {self.index_dir}")
         return None, None, None
+
+    def _load_index_file(self, f):
+        """One GPU: the whole file.  Under torchrun (torch.distributed initialised, world > 1): this
+        rank's row range, searched SPMD with a top-k exchange (image_recommender_b200.sharded) — every
+        rank must then issue the same queries."""
+        try:
+            import torch.distributed as dist
+            sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except Exception:
+            sharded = False
+        if not sharded:
+            return FlatShard.load(f, device=self.device)
+        from image_recommender_b200.sharded import ShardedIndex
+        return ShardedIndex.load(f, device=self.device)
 
     def _fetch_results(self, indices, distances, offset_table):
         conn = sqlite3.connect(self.db_path)
@@ -416,12 +430,23 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--plot", action="store_true")
     a = ap.parse_args(argv)
+    import os
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:       # torchrun --nproc-per-node G -m main.search_from_image ...: row-sharded over G GPUs
+        import torch
+        import torch.distributed as dist
+        a.device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(a.device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", a.device))
     rec = ImageRecommender(images_root=a.images_root, db_path=a.db_path, top_k=a.top_k, index_dir=a.index_dir,
                            device=a.device)
-    results = rec.search_similar_images(a.query, index_type=a.index, plot=a.plot)
-    for fp, dist in results or []:
-        print(f"{dist:.6f}\t{fp}")
+    results = rec.search_similar_images(a.query, index_type=a.index, plot=a.plot and rank == 0)
+    if rank == 0:
+        for fp, dist_ in results or []:
+            print(f"{dist_:.6f}\t{fp}")
     rec.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0 if results else 1
 
 

@@ -182,7 +182,10 @@ def test_search_auto_path_and_fallback_tc(db20k):
     ix, pk, n = db20k
     _set_path(ix, "auto")
     q = oracle.synth_queries(DIMS, 200, n, n_clusters=8, qseed=99)
-    assert _check(ix, pk, q[:1], 10)["path"] == 1
+    assert _check(ix, pk, q[:1], 10)["path"] == 2        # tcgen05 at every batch size (measured faster)
+    ix.set_option(_capi.OPT_SCAN_MAX_B, 4)
+    assert _check(ix, pk, q[:3], 10)["path"] == 1        # K-scan on request
+    ix.set_option(_capi.OPT_SCAN_MAX_B, 0)
     assert _check(ix, pk, q[:9], 10)["path"] == 2
     assert _check(ix, pk, q, 10)["path"] == 3
     q = q[:9]
@@ -297,9 +300,8 @@ def test_near_duplicate_runs_are_collected(gpu, path):
 
 @pytest.mark.parametrize("dims,n", [([32768], 700), ([4096, 64], 1500), ([128], 5000)])
 def test_other_baseline_dims_match_oracle(gpu, dims, n):
-    """BASELINE configs 4 / 4s: the raw 32768-d SIFT-VLAD descriptor (wider than K-scan's register
-    budget: every batch size takes the tcgen05 path), a wide two-table combo, and the stored 128-d
-    table.  Pack, batch-1 and batch-130 search bit-equal to the oracle."""
+    """BASELINE configs 4 / 4s: the raw 32768-d SIFT-VLAD descriptor, a wide two-table combo, and the
+    stored 128-d table.  Pack, batch-1 and batch-130 search bit-equal to the oracle."""
     irb = _irb()
     tabs, pk = _mk(n, dims)
     ix = irb.FlatShard(dims, n, device=gpu)
@@ -308,7 +310,7 @@ def test_other_baseline_dims_match_oracle(gpu, dims, n):
     assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32)) and np.array_equal(b, pk["bf16"])
     q = oracle.synth_queries(dims, 130, n, n_clusters=8, qseed=77)
     st1 = _check(ix, pk, q[:1], 10)
-    assert st1["path"] == (1 if sum(dims) <= 4096 else 2)
+    assert st1["path"] == 2
     st = _check(ix, pk, q, 10)
     assert st["path"] == 3 and st["n_uncertified"] == 0
     ix.close()
@@ -442,7 +444,7 @@ def test_other_baseline_configs(gpu, dims, n, nq, k):
     assert np.array_equal(f.view(np.uint32), pk["f32"].view(np.uint32)) and np.array_equal(b, pk["bf16"])
     q = oracle.synth_queries(dims, nq, n, n_clusters=8, abs_mask=1 if dims[0] == 48 else 0)
     st = _check(ix, pk, q, k)
-    assert st["path"] == (1 if nq == 1 and sum(dims) <= 4096 else (3 if nq > 128 else 2))
+    assert st["path"] == (3 if nq > 128 else 2)
     ix.close()
 
 
