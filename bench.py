@@ -33,6 +33,8 @@ UNIT = "queries/s"
 # side workloads for `--config`.  per_gpu: the config only fits a box of 8, so with fewer GPUs the
 # database is cut to that many rows per GPU (weak scaling; the row count used is in the JSON line).
 CONFIGS = {
+    "1": dict(dims=[48], rows=10_000, batch=1, per_gpu=None, k=5, hnsw_rows=10_000,
+              name="color histogram (48), the reference's own CPU-runnable case"),
     "2": dict(dims=[1792], rows=1_000_000, batch=1000, per_gpu=None, name="DreamSim-only (1792)"),
     "3": dict(dims=[48, 128, 1792], rows=10_000_000, batch=4096, per_gpu=None,
               name="combo color+sift+dreamsim (48+128+1792)"),
@@ -54,6 +56,12 @@ def apply_config(args):
         args.rows = rows
     if args.batch is None:
         args.batch = c["batch"]
+    if "k" in c and args.k is None:
+        args.k = c["k"]
+    if args.k is None:
+        args.k = 10
+    if c.get("hnsw_rows") and args.hnsw_rows == 0:
+        args.hnsw_rows = c["hnsw_rows"]
     args.workload_name = c["name"]
     args.scaling = "weak" if c["per_gpu"] and rows < c["rows"] else "strong"
     if args.config != "3":
@@ -69,7 +77,7 @@ def parse_args():
     ap.add_argument("--config", default="3", choices=sorted(CONFIGS), help="BASELINE.json config (default 3: the headline)")
     ap.add_argument("--rows", type=int, default=None, help="total database rows over all ranks (default: the config's)")
     ap.add_argument("--batch", type=int, default=None, help="queries per step (default: the config's; 4096 for config 3)")
-    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--k", type=int, default=None, help="top-k (default 10; config 1: 5)")
     ap.add_argument("--sweep", default="", help="comma-separated extra batch sizes reported under 'sweep'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

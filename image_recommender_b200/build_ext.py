@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     # the default host compiler wrapper of this image lacks a few spec files; use the system g++
     ccbin = ["-ccbin", "/usr/bin/g++"] if Path("/usr/bin/g++").exists() else []
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("B2K_NVCC_EXTRA", "").split()
 
     def compile_one(src: str) -> Path:
         obj = obj_dir / (src[:-3] + ".o")

@@ -230,7 +230,11 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
       if (rc) return rc;
       ix->tmap_q_ptr = w.q_bf16; ix->tmap_q_rows = nq_pad;
     }
-    const bool pair = ix->opt_pair < 0 ? nq > 128 : ix->opt_pair != 0;
+    // CTA pairs work on 256-query tiles: when the last one would be at most half full (3, 5 or 7
+    // tiles of 128) the single-CTA kernel wastes no tensor work and measures 6-40 % faster
+    // (gpurun_out/exp_mid.log); from 1024 queries on the pair kernel's lower operand traffic wins.
+    const int n_qt128 = (nq + 127) / 128;
+    const bool pair = ix->opt_pair < 0 ? (nq > 128 && !((n_qt128 & 1) && n_qt128 <= 7)) : ix->opt_pair != 0;
     const int forced = std::min(ix->opt_splits, w.n_lists);
     ScoreTcArgs ta;
     ta.tmap_q = &ix->tmap_q; ta.tmap_db = pair ? &ix->tmap_db2 : &ix->tmap_db;
@@ -275,7 +279,10 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   se.partial = w.partial; se.n_lists = n_lists_used; se.list_stride = w.n_lists; se.k = k; se.eps = eps;
   se.cand_cap = w.cand_cap; se.force_exact = ix->opt_force_exact;
   se.cand_rows = w.cand_rows; se.cand_count = w.cand_count; se.flags = w.flags; se.thr = w.thr;
-  se.db_f32 = ix->opt_tighten ? ix->f32 : nullptr; se.q = q_dev; se.D = ix->D;
+  // tightening trades 2 x k latency-bound row gathers per query (25 us at batch 1) for ~3x fewer rows
+  // to re-rank: a win once the re-rank is throughput-bound, a loss for the latency of small batches
+  const bool tighten = ix->opt_tighten > 1 || (ix->opt_tighten == 1 && nq >= 256);
+  se.db_f32 = tighten ? ix->f32 : nullptr; se.q = q_dev; se.D = ix->D;
   se.lb = w.lb; se.sat_count = w.fail_count + 1; se.sat_pairs = ix->opt_collect ? w.sat_pairs : nullptr;
   se.sat_cap = ix->opt_collect ? w.sat_cap : 0;
   rc = launch_select(se, nq, st);
@@ -713,7 +720,8 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
       if (value < 0 || value > 4096) break;
       ix->opt_splits = (int)value; return 0;
     case B2K_OPT_TIGHTEN:
-      ix->opt_tighten = value != 0; return 0;
+      if (value < 0 || value > 2) break;
+      ix->opt_tighten = (int)value; return 0;
     case B2K_OPT_COLLECT:
       ix->opt_collect = value != 0; return 0;
     case B2K_OPT_SEED:
@@ -838,21 +846,40 @@ int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_en
   if (rc) { fclose(f); return rc; }
   if (ix->D != h.D) { fclose(f); b2k_destroy(ix); set_error("load: corrupt header"); return B2K_E_IO; }
   DeviceGuard g(device);
-  rc = dev_alloc(&ix->stage_rows_f32, (size_t)ix->stage_rows * ix->D);
-  std::vector<float> buf((size_t)std::min<int64_t>(ix->stage_rows, std::max<int64_t>(n, 1)) * ix->D);
+  // file -> pinned slot (fread) -> async H2D -> re-pack; the read of chunk i+1 overlaps the DMA and
+  // the pack of chunk i (one device staging buffer: copies and packs are ordered on the stream)
+  const int64_t chunk = std::max<int64_t>(256, std::min<int64_t>(ix->stage_rows, ((int64_t)1 << 26) / ((int64_t)ix->D * 4)));
+  rc = dev_alloc(&ix->stage_rows_f32, (size_t)chunk * ix->D);
+  float* pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool busy[2] = {false, false};
+  for (int s = 0; s < 2 && !rc; ++s) {
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&pin[s]), (size_t)chunk * ix->D * 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming);
+    if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; }
+  }
   if (!rc && fseek(f, (long)(h.rows_offset + row_begin * (int64_t)ix->D * 4), SEEK_SET) != 0) { set_error("load: seek failed"); rc = B2K_E_IO; }
-  for (int64_t r0 = 0; !rc && r0 < n; r0 += ix->stage_rows) {
-    const int64_t m = std::min(ix->stage_rows, n - r0);
-    if (fread(buf.data(), (size_t)ix->D * 4, (size_t)m, f) != (size_t)m) { set_error("load: short read in %s", path); rc = B2K_E_IO; break; }
-    cudaError_t e = cudaMemcpyAsync(ix->stage_rows_f32, buf.data(), (size_t)m * ix->D * 4, cudaMemcpyHostToDevice, ix->stream);
+  int slot = 0;
+  for (int64_t r0 = 0; !rc && r0 < n; r0 += chunk, slot ^= 1) {
+    const int64_t m = std::min(chunk, n - r0);
+    cudaError_t e = cudaSuccess;
+    if (busy[slot]) { e = cudaEventSynchronize(ev[slot]); busy[slot] = false; }
+    if (e == cudaSuccess && fread(pin[slot], (size_t)ix->D * 4, (size_t)m, f) != (size_t)m) { set_error("load: short read in %s", path); rc = B2K_E_IO; break; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->stage_rows_f32, pin[slot], (size_t)m * ix->D * 4, cudaMemcpyHostToDevice, ix->stream);
     if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; break; }
     // stored rows are already normalised: re-pack without scaling (same per-table sums -> same norm2 bits)
     PackArgs a;
     fill_pack_args(ix, a, m, r0, 0);
     for (int t = 0; t < ix->n_tables; ++t) { a.tables[t] = ix->stage_rows_f32 + ix->col_off[t]; a.strides[t] = ix->D; }
     rc = launch_pack(a, ix->stream);
-    if (!rc) { e = cudaStreamSynchronize(ix->stream); if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; } }
+    if (!rc) { e = cudaEventRecord(ev[slot], ix->stream); busy[slot] = true; if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; } }
   }
+  {
+    cudaError_t e = cudaStreamSynchronize(ix->stream);
+    if (!rc && e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; }
+  }
+  for (int s = 0; s < 2; ++s) { if (pin[s]) cudaFreeHost(pin[s]); if (ev[s]) cudaEventDestroy(ev[s]); }
+  dev_free(ix->stage_rows_f32);
   fclose(f);
   if (rc) { b2k_destroy(ix); return rc; }
   ix->ntotal = n;

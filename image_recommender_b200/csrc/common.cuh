@@ -105,6 +105,44 @@ __device__ __forceinline__ float lane_sumsq(const float* __restrict__ x, int d, 
   return p;
 }
 
+// Lane-partial of Spec R's exact score: fp32 products accumulated in fp64, element i owned by lane
+// (i/4) % 32 and folded in increasing i (combine the lanes with warp_sum_f64, round once to fp32).
+// The row is a latency-bound gather, so eight 16-byte loads per lane are issued before the dependent
+// fp64 chain consumes them; the FMA order is unchanged.
+__device__ __forceinline__ double lane_dot64(const float* __restrict__ q, const float* __restrict__ x, int d, int lane) {
+  double p = 0.0;
+  const bool vec = ((d & 3) == 0) && (((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(x)) & 15) == 0);
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    const int n4 = d >> 2;
+    int i = lane;
+    for (; i + 7 * 32 < n4; i += 8 * 32) {
+      float4 v[8], w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { v[u] = __ldg(x4 + i + u * 32); w[u] = __ldg(q4 + i + u * 32); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        p = __fma_rn((double)w[u].x, (double)v[u].x, p); p = __fma_rn((double)w[u].y, (double)v[u].y, p);
+        p = __fma_rn((double)w[u].z, (double)v[u].z, p); p = __fma_rn((double)w[u].w, (double)v[u].w, p);
+      }
+    }
+    for (; i < n4; i += 32) {
+      const float4 v = __ldg(x4 + i), w = __ldg(q4 + i);
+      p = __fma_rn((double)w.x, (double)v.x, p); p = __fma_rn((double)w.y, (double)v.y, p);
+      p = __fma_rn((double)w.z, (double)v.z, p); p = __fma_rn((double)w.w, (double)v.w, p);
+    }
+  } else {
+    for (int i4 = lane; i4 * 4 < d; i4 += 32)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i4 * 4 + c;
+        if (i < d) p = __fma_rn((double)q[i], (double)x[i], p);
+      }
+  }
+  return p;
+}
+
 __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
   return __bfloat16_as_ushort(__float2bfloat16_rn(f));
 }

@@ -128,17 +128,39 @@ query_prep_kernel(QueryPrepArgs a) {
   const float* q = a.q + (int64_t)w * a.D;
   const float qn2 = warp_sum_f32(lane_sumsq(q, a.D, lane));
   float pb = 0.f, pd = 0.f;
-  for (int i = lane; i < a.Dp; i += 32) {
-    uint16_t b = 0;
-    if (i < a.D) {
-      const float v = q[i];
-      b = f32_to_bf16_bits(v);
-      const float vb = bf16_bits_to_f32(b);
-      pb = __fmaf_rn(vb, vb, pb);
-      const float df = __fsub_rn(vb, v);
-      pd = __fmaf_rn(df, df, pd);
+  const bool vec = ((a.D & 3) == 0) && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+  if (vec) {
+    // 4 elements per lane and step (16-byte loads, 8-byte bf16 stores); Dp is a multiple of 64
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    for (int c = lane; c < (a.Dp >> 2); c += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < (a.D >> 2)) v = q4[c];
+      const uint16_t b0 = f32_to_bf16_bits(v.x), b1 = f32_to_bf16_bits(v.y);
+      const uint16_t b2 = f32_to_bf16_bits(v.z), b3 = f32_to_bf16_bits(v.w);
+      const float f0 = bf16_bits_to_f32(b0), f1 = bf16_bits_to_f32(b1), f2 = bf16_bits_to_f32(b2), f3 = bf16_bits_to_f32(b3);
+      pb = __fmaf_rn(f0, f0, pb); pb = __fmaf_rn(f1, f1, pb); pb = __fmaf_rn(f2, f2, pb); pb = __fmaf_rn(f3, f3, pb);
+      const float d0 = __fsub_rn(f0, v.x), d1 = __fsub_rn(f1, v.y), d2 = __fsub_rn(f2, v.z), d3 = __fsub_rn(f3, v.w);
+      pd = __fmaf_rn(d0, d0, pd); pd = __fmaf_rn(d1, d1, pd); pd = __fmaf_rn(d2, d2, pd); pd = __fmaf_rn(d3, d3, pd);
+      if (ob) {
+        uint2 pk;
+        pk.x = (uint32_t)b0 | ((uint32_t)b1 << 16);
+        pk.y = (uint32_t)b2 | ((uint32_t)b3 << 16);
+        *reinterpret_cast<uint2*>(ob + 4 * c) = pk;
+      }
     }
-    if (ob) ob[i] = b;
+  } else {
+    for (int i = lane; i < a.Dp; i += 32) {
+      uint16_t b = 0;
+      if (i < a.D) {
+        const float v = q[i];
+        b = f32_to_bf16_bits(v);
+        const float vb = bf16_bits_to_f32(b);
+        pb = __fmaf_rn(vb, vb, pb);
+        const float df = __fsub_rn(vb, v);
+        pd = __fmaf_rn(df, df, pd);
+      }
+      if (ob) ob[i] = b;
+    }
   }
   const float qb2 = warp_sum_f32(pb), qd2 = warp_sum_f32(pd);
   if (lane == 0) {

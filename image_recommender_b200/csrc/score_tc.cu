@@ -152,7 +152,13 @@ ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) {
   ScoreTcPlan p;
   p.n_qtiles = (nq + kBlockM - 1) / kBlockM;
   const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
-  int splits = forced_splits > 0 ? forced_splits : n_sm;
+  // one CTA per SM is resident.  Long splits (>= 128 tiles): one split per SM, the query tiles of a
+  // split run back to back.  Short splits: a single wave of n_qtiles * n_splits <= n_sm CTAs, so the
+  // per-CTA pipeline fill / last epilogue is paid once (the query tiles of a split then run
+  // concurrently and share the DB tiles through L2).
+  int splits = n_sm;
+  if (forced_splits > 0) splits = forced_splits;
+  else if (p.n_qtiles > 1 && tiles_total / n_sm < 128) splits = n_sm / p.n_qtiles > 0 ? n_sm / p.n_qtiles : 1;
   if ((int64_t)splits > tiles_total) splits = (int)(tiles_total > 0 ? tiles_total : 1);
   p.n_splits = splits;
   p.grid = p.n_qtiles * p.n_splits;

@@ -18,6 +18,18 @@
 
 namespace b2k {
 
+#ifdef B2K_PHASE_TIMERS
+// debug build only (scripts/exp_phase.py): %globaltimer at the phase boundaries of select_kernel, CTA 0
+__device__ unsigned long long g_phase_t[16];
+#define B2K_PHASE(i) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; \
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_phase_t[i] = t_; } } while (0)
+extern "C" int b2k_debug_phase_times(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_phase_t, sizeof(g_phase_t));
+}
+#else
+#define B2K_PHASE(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kSelThreads = 256;
@@ -67,9 +79,23 @@ __device__ __forceinline__ void block_topk_u64(const uint64_t* keys, int n, int 
 
 // Partial-list entries as distinct u64 keys: (order-preserving score key << 32) | reversed slot.
 __device__ __forceinline__ void load_list_keys(const Cand* lst, int E, uint64_t* keys) {
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+  // four independent 8-byte loads in flight per thread: the lists were just written by the scoring
+  // kernel and come from L2 (a dependent one-at-a-time loop costs 6 us per 4736 entries at batch 1)
+  const int T = blockDim.x;
+  int e = threadIdx.x;
+  for (; e + 3 * T < E; e += 4 * T) {
+    Cand c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = lst[e + u * T];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t fk = c[u].row < 0 ? 0u : float_key(c[u].score);     // NaN scores -> 0: dropped
+      keys[e + u * T] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - (e + u * T))) : 0ull;
+    }
+  }
+  for (; e < E; e += T) {
     const Cand c = lst[e];
-    const uint32_t fk = c.row < 0 ? 0u : float_key(c.score);     // NaN scores -> 0: dropped
+    const uint32_t fk = c.row < 0 ? 0u : float_key(c.score);
     keys[e] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - e)) : 0ull;
   }
   __syncthreads();
@@ -96,11 +122,14 @@ select_kernel(SelectArgs a) {
   const Cand* lst = a.partial + (int64_t)q * a.list_stride * kList;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { s_count = 0; s_sat = 0; }
+  B2K_PHASE(0);
   load_list_keys(lst, E, skey);
+  B2K_PHASE(1);
 
   // b_k = k-th best approximate score over every list; 0: fewer than k rows listed -> everything
   // listed is a candidate.
   block_topk_u64(skey, E, a.k, wtop, top);
+  B2K_PHASE(2);
   const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
   float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
   // lower bound of the exact k-th best score: the k best approximate rows have exact >= b_k - eps
@@ -116,13 +145,7 @@ select_kernel(SelectArgs a) {
     for (int j = warp; j < a.k; j += (kSelThreads >> 5)) {
       const int e = E - 1 - (int)(uint32_t)(top[j] & 0xffffffffull);
       const float* x = a.db_f32 + (int64_t)lst[e].row * a.D;
-      double p = 0.0;
-      for (int i4 = lane; i4 * 4 < a.D; i4 += 32)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int i = i4 * 4 + c;
-          if (i < a.D) p = __fma_rn((double)qv[i], (double)x[i], p);
-        }
+      const double p = lane_dot64(qv, x, a.D, lane);
       const float sj = (float)warp_sum_f64(p);
       if (lane == 0) s_exact[j] = sj;
     }
@@ -133,6 +156,7 @@ select_kernel(SelectArgs a) {
     if (t2 > thr) { thr = t2; lb = smin; }      // NaN-safe: keeps the looser bound
   }
 
+  B2K_PHASE(3);
   // candidates + saturation, from the shared-memory keys (rows are fetched for hits only).
   // Warp w owns lists w, w+8, ...; lane j = entry j of the list.
   const uint32_t thr_key = float_key(thr);              // score >= thr  <=>  key >= thr_key
@@ -164,6 +188,7 @@ select_kernel(SelectArgs a) {
     }
   }
   __syncthreads();
+  B2K_PHASE(4);
   if (tid == 0) {
     int cnt = s_count;
     int flag = 0;
@@ -206,30 +231,9 @@ rerank_kernel(RerankArgs a) {
   const int w0 = blockIdx.x * wpb + (threadIdx.x >> 5);
   const int wstride = gridDim.x * wpb;
   const float* __restrict__ qv = a.q + (int64_t)q * a.D;
-  const bool vec = ((a.D & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(a.db_f32) & 15) == 0);
   for (int c = w0; c < cnt; c += wstride) {
     const int32_t row = a.cand_rows[(int64_t)q * a.cand_cap + c];
-    const float* __restrict__ x = a.db_f32 + (int64_t)row * a.D;
-    double p = 0.0;
-    if (vec) {
-      const float4* x4 = reinterpret_cast<const float4*>(x);
-      const float4* q4 = reinterpret_cast<const float4*>(qv);
-      for (int i = lane; i < (a.D >> 2); i += 32) {
-        const float4 v = __ldg(x4 + i);
-        const float4 w = __ldg(q4 + i);
-        p = __fma_rn((double)w.x, (double)v.x, p);
-        p = __fma_rn((double)w.y, (double)v.y, p);
-        p = __fma_rn((double)w.z, (double)v.z, p);
-        p = __fma_rn((double)w.w, (double)v.w, p);
-      }
-    } else {
-      for (int i4 = lane; i4 * 4 < a.D; i4 += 32)
-        for (int j = 0; j < 4; ++j) {
-          const int i = i4 * 4 + j;
-          if (i < a.D) p = __fma_rn((double)qv[i], (double)x[i], p);
-        }
-    }
+    const double p = lane_dot64(qv, a.db_f32 + (int64_t)row * a.D, a.D, lane);
     const float ip = (float)warp_sum_f64(p);
     if (lane == 0) a.cand_ip[(int64_t)q * a.cand_cap + c] = ip;
   }

@@ -167,7 +167,7 @@ def test_threshold_tightening_keeps_bits_and_cuts_candidates_tc(db20k):
     for path in ("scan", "tc2"):
         _set_path(ix, path)
         for on in (0, 1):
-            ix.set_option(_capi.OPT_TIGHTEN, on)
+            ix.set_option(_capi.OPT_TIGHTEN, 2 * on)          # 2 = always (1 = auto: only from 256 queries)
             st = _check(ix, pk, q[:4] if path == "scan" else q, 10)
             cands[(path, on)] = st["n_candidates"] / st["n_queries"]
             assert st["n_uncertified"] == 0
@@ -187,7 +187,9 @@ def test_search_auto_path_and_fallback_tc(db20k):
     assert _check(ix, pk, q[:3], 10)["path"] == 1        # K-scan on request
     ix.set_option(_capi.OPT_SCAN_MAX_B, 0)
     assert _check(ix, pk, q[:9], 10)["path"] == 2
-    assert _check(ix, pk, q, 10)["path"] == 3
+    assert _check(ix, pk, q, 10)["path"] == 3            # 200 queries = one full 256-query pair tile
+    q300 = oracle.synth_queries(DIMS, 300, n, n_clusters=8, qseed=98)
+    assert _check(ix, pk, q300, 10)["path"] == 2         # 3 tiles of 128: a pair tile would be half empty
     q = q[:9]
     # exhaustive fp32 scan (the route of uncertified queries) returns the same bits
     ix.set_option(_capi.OPT_FORCE_EXACT, 1)
