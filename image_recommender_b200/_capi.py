@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libb2k.so"
 
 B2K_MAX_TABLES = 8
-B2K_MAX_K = 32
+B2K_MAX_K = 1024
 B2K_LIST = 32
 
 OPT_PATH, OPT_RERANK, OPT_FORCE_EXACT, OPT_SCAN_MAX_B, OPT_SPLITS, OPT_TC_PAIR, OPT_SEED, OPT_TIGHTEN, OPT_COLLECT = 1, 2, 3, 4, 5, 6, 7, 8, 9

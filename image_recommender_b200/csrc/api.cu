@@ -50,7 +50,8 @@ template <typename T>
 void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
 struct Workspace {
-  int nq_cap = 0, n_lists = 0, cand_cap = 0, exact_splits = 0;
+  int nq_cap = 0, n_lists = 0, cand_cap = 0, exact_splits = 0, k_cap = 0;
+  unsigned long long* exact_ceil = nullptr;   // [nq] K-exact paging: key of the last emitted result per failed slot
   float* q = nullptr;             // [nq, D] staging for the host API
   uint16_t* q_bf16 = nullptr;     // [nq_pad, Dp]
   float *qn2 = nullptr, *eps_scan = nullptr, *eps_tc = nullptr, *thr = nullptr, *thr_floor = nullptr, *lb = nullptr;
@@ -65,7 +66,7 @@ struct Workspace {
   int64_t* out_labels = nullptr;
   void release() {
     dev_free(q); dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr); dev_free(thr_floor);
-    dev_free(lb); dev_free(sat_pairs);
+    dev_free(lb); dev_free(sat_pairs); dev_free(exact_ceil);
     dev_free(partial); dev_free(cand_rows); dev_free(cand_count); dev_free(flags); dev_free(cand_ip);
     dev_free(fail_count); dev_free(fail_list); dev_free(exact_partial);
     dev_free(out_ip); dev_free(out_dist); dev_free(out_labels);
@@ -142,14 +143,20 @@ void fill_pack_args(const b2k_index* ix, PackArgs& a, int64_t n, int64_t row0, i
   a.out_f32 = ix->f32; a.out_bf16 = ix->bf16; a.out_norm2 = ix->norm2; a.stat_bits = ix->stat_bits;
 }
 
-int ensure_workspace(b2k_index* ix, int nq) {
+// Partial lists hold 32 entries per (query, DB split): the split count grows with k so that the lists
+// offer ~8 slots per wanted neighbour (k <= 592: one split per SM as ever; up to 1024: two per SM).
+int min_splits_for_k(int k) { return k <= kList ? 0 : (k + 3) / 4; }
+
+int ensure_workspace(b2k_index* ix, int nq, int k) {
   Workspace& w = ix->ws;
   const int scan_lists = scan_num_splits(ix->n_sm);
   const int tc_lists = ix->n_sm;
-  const int n_lists = std::max(scan_lists, tc_lists);
+  int n_lists = std::max(scan_lists, tc_lists);
+  while (n_lists < min_splits_for_k(k)) n_lists += ix->n_sm;
   const int exact_splits = exact_num_splits(ix->n_sm);
   const int cand_cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : n_lists * kList;
-  if (nq <= w.nq_cap && w.n_lists == n_lists && w.cand_cap == cand_cap) return 0;
+  const int k_cap = std::max(k, (int)kList);
+  if (nq <= w.nq_cap && w.n_lists == n_lists && w.cand_cap == cand_cap && k_cap <= w.k_cap) return 0;
   B2K_CUDA(cudaStreamSynchronize(ix->stream));
   w.release();
   const int cap = std::max(nq, 8);
@@ -173,10 +180,11 @@ int ensure_workspace(b2k_index* ix, int nq) {
   if ((rc = dev_alloc(&w.fail_count, 2))) return rc;      // [0] failed queries, [1] saturated pairs
   if ((rc = dev_alloc(&w.fail_list, cap))) return rc;
   if ((rc = dev_alloc(&w.exact_partial, (size_t)cap * exact_splits * kList))) return rc;
-  if ((rc = dev_alloc(&w.out_ip, (size_t)cap * B2K_MAX_K))) return rc;
-  if ((rc = dev_alloc(&w.out_dist, (size_t)cap * B2K_MAX_K))) return rc;
-  if ((rc = dev_alloc(&w.out_labels, (size_t)cap * B2K_MAX_K))) return rc;
-  w.nq_cap = cap; w.n_lists = n_lists; w.cand_cap = cand_cap; w.exact_splits = exact_splits;
+  if ((rc = dev_alloc(&w.exact_ceil, cap))) return rc;
+  if ((rc = dev_alloc(&w.out_ip, (size_t)cap * k_cap))) return rc;
+  if ((rc = dev_alloc(&w.out_dist, (size_t)cap * k_cap))) return rc;
+  if ((rc = dev_alloc(&w.out_labels, (size_t)cap * k_cap))) return rc;
+  w.nq_cap = cap; w.n_lists = n_lists; w.cand_cap = cand_cap; w.exact_splits = exact_splits; w.k_cap = k_cap;
   ix->tmap_q_ptr = nullptr;   // q_bf16 moved
   return 0;
 }
@@ -236,10 +244,12 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     const int n_qt128 = (nq + 127) / 128;
     const bool pair = ix->opt_pair < 0 ? (nq > 128 && !((n_qt128 & 1) && n_qt128 <= 7)) : ix->opt_pair != 0;
     const int forced = std::min(ix->opt_splits, w.n_lists);
+    const int min_splits = std::min(min_splits_for_k(k), w.n_lists);
     ScoreTcArgs ta;
     ta.tmap_q = &ix->tmap_q; ta.tmap_db = pair ? &ix->tmap_db2 : &ix->tmap_db;
     ta.n_rows = ix->ntotal; ta.Dp = ix->Dp; ta.nq = nq;
-    ta.plan = pair ? score_tc2_plan(nq, ix->ntotal, ix->n_sm, forced) : score_tc_plan(nq, ix->ntotal, ix->n_sm, forced);
+    ta.plan = pair ? score_tc2_plan(nq, ix->ntotal, ix->n_sm, forced, min_splits)
+                   : score_tc_plan(nq, ix->ntotal, ix->n_sm, forced, min_splits);
     ta.partial = w.partial; ta.n_lists = w.n_lists; ta.max_tiles = 0; ta.thr_floor = nullptr;
     // Threshold seeding: a sampling pass over the first tiles of every split bounds each query's
     // k-th best score from below, so the full pass admits only rows that can still matter and
@@ -320,10 +330,15 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   ea.db_f32 = ix->f32; ea.norm2 = ix->norm2; ea.n_rows = ix->ntotal; ea.D = ix->D; ea.q = q_dev;
   ea.qn2 = w.qn2; ea.nq = nq; ea.k = k; ea.base_offset = ix->base; ea.fail_count = w.fail_count;
   ea.fail_list = w.fail_list; ea.partial = w.exact_partial; ea.n_splits = w.exact_splits;
-  ea.out_ip = ip_dev; ea.out_dist = dist_dev; ea.out_labels = labels_dev;
-  rc = launch_exact(ea, st);
-  if (rc) return rc;
-  launches += 2;
+  ea.out_ip = ip_dev; ea.out_dist = dist_dev; ea.out_labels = labels_dev; ea.ceil_keys = w.exact_ceil;
+  // the exhaustive scan keeps 32 results per pass: k > 32 is served in pages, each page scanning for
+  // the rows strictly after the last result of the page before
+  for (int page = 0; page * kList < k; ++page) {
+    ea.page = page;
+    rc = launch_exact(ea, st);
+    if (rc) return rc;
+    launches += 2;
+  }
   B2K_CUDA(cudaEventRecord(ix->ev[2], st));
   ix->ev_valid = true;
 
@@ -339,6 +354,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
 int check_search_args(const b2k_index* ix, const void* q, int nq, int k, const void* dist, const void* labels) {
   if (!ix || !q || !dist || !labels || nq <= 0 || k <= 0) { set_error("search: bad argument"); return B2K_E_INVALID; }
   if (k > B2K_MAX_K) { set_error("search: k=%d exceeds B2K_MAX_K=%d", k, B2K_MAX_K); return B2K_E_INVALID; }
+  if (k > kList && ix->opt_cand_cap > 0) { set_error("search: B2K_OPT_RERANK budgets apply to k <= %d only", (int)kList); return B2K_E_INVALID; }
   return 0;
 }
 
@@ -616,7 +632,7 @@ int b2k_search_device(b2k_index* ix, const float* q_dev, int32_t nq, int32_t k, 
   if (rc) return rc;
   DeviceGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;      // NULL = the legacy default stream, as given
-  rc = ensure_workspace(ix, std::min(nq, kMaxNqPerPass));
+  rc = ensure_workspace(ix, std::min(nq, kMaxNqPerPass), k);
   if (rc) return rc;
   for (int q0 = 0; q0 < nq; q0 += kMaxNqPerPass) {
     const int m = std::min(kMaxNqPerPass, nq - q0);
@@ -632,7 +648,7 @@ int b2k_search(b2k_index* ix, const float* q_host, int32_t nq, int32_t k, float*
   int rc = check_search_args(ix, q_host, nq, k, dist_host, labels_host);
   if (rc) return rc;
   DeviceGuard g(ix->device);
-  rc = ensure_workspace(ix, std::min(nq, kMaxNqPerPass));
+  rc = ensure_workspace(ix, std::min(nq, kMaxNqPerPass), k);
   if (rc) return rc;
   Workspace& w = ix->ws;
   cudaStream_t st = ix->stream;
@@ -740,7 +756,7 @@ int b2k_merge_topk_device(const float* ip, const float* dist, const int64_t* lab
                           int32_t nq, int32_t k, float* out_ip, float* out_dist, int64_t* out_labels,
                           int32_t device, void* stream) {
   if (!ip || !dist || !labels || !out_dist || !out_labels || n_lists < 1 || nq < 0 || k < 1 || k > B2K_MAX_K ||
-      n_lists * k > 1024) {
+      (n_lists > 32 && n_lists * k > 1024)) {
     set_error("merge: bad argument");
     return B2K_E_INVALID;
   }

@@ -143,6 +143,75 @@ __device__ __forceinline__ double lane_dot64(const float* __restrict__ q, const 
   return p;
 }
 
+// G-way merge (G <= 32) of per-shard result lists, each already in the global order (higher ip, then
+// lower offset) with label < 0 padding at its end: one warp per query, lane g walks list g, every
+// step is one warp arg-best.  O(k log G) for any k.  addr(g, j) = flat index of entry j of list g.
+template <typename Addr>
+__device__ __forceinline__ void warp_merge_sorted(const float* __restrict__ ip, const float* __restrict__ dist,
+                                                  const int64_t* __restrict__ lab, Addr addr, int G, int k, int lane,
+                                                  float* out_ip, float* out_dist, int64_t* out_lab) {
+  int h = 0;
+  uint32_t key = 0u;
+  int64_t off = INT64_MAX, src = -1;
+  bool valid = false;
+  auto load = [&]() {
+    valid = lane < G && h < k;
+    if (valid) {
+      src = addr(lane, h);
+      off = lab[src];
+      valid = off >= 0;
+      if (valid) key = float_key(ip[src]);
+    }
+  };
+  load();
+  for (int j = 0; j < k; ++j) {
+    uint32_t bk = valid ? key : 0u;
+    int64_t bo = valid ? off : INT64_MAX;
+    int bl = valid ? lane : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int64_t oo = __shfl_xor_sync(0xffffffffu, bo, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      const bool take = ol >= 0 && (bl < 0 || ok > bk || (ok == bk && (oo < bo || (oo == bo && ol < bl))));
+      if (take) { bk = ok; bo = oo; bl = ol; }
+    }
+    if (bl < 0) {                      // every list is exhausted: faiss-style padding
+      if (lane == 0) {
+        if (out_ip) out_ip[j] = -3.402823466e38f;
+        out_dist[j] = 3.402823466e38f;
+        out_lab[j] = -1;
+      }
+      continue;
+    }
+    if (lane == bl) {
+      if (out_ip) out_ip[j] = ip[src];
+      out_dist[j] = dist[src];
+      out_lab[j] = off;
+      ++h;
+      load();
+    }
+  }
+}
+
+// Block-wide bitonic sort of P (a power of two) u64 keys in shared memory, descending; 0 = empty
+// slot, sorts last.  All threads of the block must call.
+__device__ __forceinline__ void block_bitonic_desc(uint64_t* keys, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool desc = (i & k) == 0;
+          const uint64_t x = keys[i], y = keys[ixj];
+          if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
   return __bfloat16_as_ushort(__float2bfloat16_rn(f));
 }

@@ -139,6 +139,8 @@ struct ExactArgs {
   Cand* partial;          // [max_fail_slots, n_splits, kList] exact scores
   int32_t n_splits;
   float* out_ip; float* out_dist; int64_t* out_labels;
+  unsigned long long* ceil_keys;   // [max_fail_slots] paging state: key of the last result emitted per failed slot
+  int32_t page;                    // results [32*page, 32*page + 32) of every failed query
 };
 
 struct MergeArgs {
@@ -193,12 +195,12 @@ struct SeedArgs {
 int launch_seed(const SeedArgs& a, int nq, cudaStream_t st);
 bool score_tc_supports(int Dp);
 int score_tc_tile_rows();      // DB rows per accumulator tile: split boundaries are multiples of it
-ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits);
+ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, int min_splits);
 int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_bf16, int nq_pad,
                          const uint16_t* db_bf16, int64_t n_rows, int Dp);
 int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st);
 // CTA-pair variant (score_tc2.cu): 256 queries per pair, DB tile halves of 128 rows per CTA
-ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits);
+ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, int min_splits);
 int score_tc2_encode_db_map(void* tmap_db_out, const uint16_t* db_bf16, int64_t n_rows, int Dp);
 int launch_score_tc2(const ScoreTcArgs& a, cudaStream_t st);
 

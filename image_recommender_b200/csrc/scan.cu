@@ -327,21 +327,6 @@ namespace {
 constexpr int kExactFQ = 4;
 constexpr int kExactWarps = 8;
 
-__device__ __forceinline__ void block_bitonic_desc(uint64_t* keys, int P) {
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const bool desc = (i & k) == 0;
-          const uint64_t x = keys[i], y = keys[ixj];
-          if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
 }  // namespace
 
 __global__ void __launch_bounds__(kExactWarps * 32)
@@ -356,11 +341,13 @@ exact_scan_kernel(ExactArgs a) {
   for (int f0 = 0; f0 < n_fail; f0 += kExactFQ) {
     const float* qp[kExactFQ];
     float e_s[kExactFQ]; int32_t e_r[kExactFQ]; float tau[kExactFQ];
+    uint64_t ceil_key[kExactFQ];      // paging (k > 32): only rows strictly after the last emitted result
 #pragma unroll
     for (int f = 0; f < kExactFQ; ++f) {
       const int fi = f0 + f < n_fail ? f0 + f : n_fail - 1;   // duplicates are harmless
       qp[f] = a.q + (int64_t)a.fail_list[fi] * a.D;
       e_s[f] = -INFINITY; e_r[f] = -1; tau[f] = -INFINITY;
+      ceil_key[f] = a.page == 0 ? ~0ull : a.ceil_keys[fi];
     }
     for (int64_t row = gw; row < a.n_rows; row += nw) {
       const float* x = a.db_f32 + row * (int64_t)a.D;
@@ -394,7 +381,7 @@ exact_scan_kernel(ExactArgs a) {
 #pragma unroll
       for (int f = 0; f < kExactFQ; ++f) {
         const float ip = (float)warp_sum_f64(p[f]);
-        if (ip > tau[f]) {   // equal scores: the earlier (lower) row already listed wins
+        if (ip > tau[f] && cand_key(ip, (int32_t)row) < ceil_key[f]) {   // equal scores: the earlier (lower) row already listed wins
           // replace the warp list's minimum (lane-per-entry, in registers)
           const uint64_t k = cand_key(e_s[f], e_r[f]);
           const uint64_t kmin = warp_min_u64(k);
@@ -441,9 +428,10 @@ exact_finalize_kernel(ExactArgs a, int P) {
   }
   __syncthreads();
   block_bitonic_desc(skeys, P);
-  if (threadIdx.x < a.k) {
-    const int j = threadIdx.x;
-    const uint64_t k = skeys[j];
+  const int j0 = a.page * kList;                      // this page emits results [j0, j0 + 32)
+  if (threadIdx.x < kList && j0 + (int)threadIdx.x < a.k) {
+    const int j = j0 + threadIdx.x;
+    const uint64_t k = skeys[threadIdx.x];
     const int32_t row = key_row(k);
     float ip = -3.402823466e38f, dist = 3.402823466e38f; int64_t lab = -1;
     if (row >= 0) {
@@ -455,6 +443,8 @@ exact_finalize_kernel(ExactArgs a, int P) {
     a.out_dist[(int64_t)q * a.k + j] = dist;
     a.out_labels[(int64_t)q * a.k + j] = lab;
   }
+  // next page continues strictly after this page's last result (0: nothing is left)
+  if (threadIdx.x == 0) a.ceil_keys[f] = skeys[kList - 1];
 }
 
 int exact_num_splits(int n_sm) { return 2 * n_sm; }

@@ -148,7 +148,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 int score_tc_tile_rows() { return kBlockN; }
 bool score_tc_supports(int Dp) { return Dp >= kBlockK && (Dp % kBlockK) == 0; }
 
-ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) {
+ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, int min_splits) {
   ScoreTcPlan p;
   p.n_qtiles = (nq + kBlockM - 1) / kBlockM;
   const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
@@ -159,6 +159,7 @@ ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) {
   int splits = n_sm;
   if (forced_splits > 0) splits = forced_splits;
   else if (p.n_qtiles > 1 && tiles_total / n_sm < 128) splits = n_sm / p.n_qtiles > 0 ? n_sm / p.n_qtiles : 1;
+  if (forced_splits <= 0 && splits < min_splits) splits = (min_splits + n_sm - 1) / n_sm * n_sm;   // k > 32: more lists
   if ((int64_t)splits > tiles_total) splits = (int)(tiles_total > 0 ? tiles_total : 1);
   p.n_splits = splits;
   p.grid = p.n_qtiles * p.n_splits;

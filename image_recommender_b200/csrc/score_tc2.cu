@@ -150,7 +150,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------
-ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) {
+ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, int min_splits) {
   ScoreTcPlan p;
   p.n_qtiles = (nq + 2 * kBlockM - 1) / (2 * kBlockM);
   const int64_t tiles_total = (n_rows + kBlockN - 1) / kBlockN;
@@ -167,10 +167,11 @@ ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits) 
     const int wave = n_sm / 2 > 0 ? n_sm / 2 : 1;
     for (int div = 1; div <= 4; div <<= 1) {
       const int s = n_sm / div;
-      if (s < 1 || n_sm % div != 0 || ((int64_t)p.n_qtiles * s) % wave != 0) continue;
+      if (s < 1 || s < min_splits || n_sm % div != 0 || ((int64_t)p.n_qtiles * s) % wave != 0) continue;
       splits = s;
       if (tiles_total / s >= 128) break;
     }
+    if (splits < min_splits) splits = (min_splits + n_sm - 1) / n_sm * n_sm;   // k > 32: more lists
   }
   if ((int64_t)splits > tiles_total) splits = (int)(tiles_total > 0 ? tiles_total : 1);
   p.n_splits = splits;

@@ -110,12 +110,37 @@ __device__ __forceinline__ float key_minus_2eps(uint32_t key, float eps) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// One CTA per query.  Dynamic smem: n_lists*32 u64 keys.
+// Tightening (both branches of select_kernel): the k rows with the best approximate scores are k
+// distinct rows, so the smallest of their EXACT scores s' is a lower bound of the exact k-th best
+// score, and every row of the exact top-k has b >= s' - eps.  s' >= b_k - eps, so this threshold is
+// never looser than b_k - 2 eps and typically one eps tighter: several times fewer rows to re-rank.
+// topk[j] = j-th best key (low word = reversed slot); s_exact: k floats of scratch.  Block-wide call.
+__device__ __forceinline__ void tighten_threshold(const SelectArgs& a, int q, const Cand* lst, int E,
+                                                  const uint64_t* topk, float* s_exact, float& thr, float& lb) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* qv = a.q + (int64_t)q * a.D;
+  for (int j = warp; j < a.k; j += (kSelThreads >> 5)) {
+    const int e = E - 1 - (int)(uint32_t)(topk[j] & 0xffffffffull);
+    const float* x = a.db_f32 + (int64_t)lst[e].row * a.D;
+    const double p = lane_dot64(qv, x, a.D, lane);
+    const float sj = (float)warp_sum_f64(p);
+    if (lane == 0) s_exact[j] = sj;
+  }
+  __syncthreads();
+  float smin = INFINITY;
+  for (int j = 0; j < a.k; ++j) smin = fminf(smin, s_exact[j]);
+  const float t2 = __fsub_rd(smin, a.eps[q]);
+  if (t2 > thr) { thr = t2; lb = smin; }      // NaN-safe: keeps the looser bound
+}
+
+// One CTA per query.  Dynamic smem: k <= 32: n_lists*32 u64 keys; k > 32: P u64 keys (P = the power of
+// two >= n_lists*32, sorted in place) + n_lists ints + k floats.
 __global__ void __launch_bounds__(kSelThreads)
-select_kernel(SelectArgs a) {
+select_kernel(SelectArgs a, int P) {
   extern __shared__ uint64_t skey[];
   __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
-  __shared__ uint64_t top[B2K_MAX_K];
+  __shared__ uint64_t top[kList];
+  __shared__ float s_exact32[kList];
   __shared__ int s_count, s_sat;
   const int q = blockIdx.x;
   const int E = a.n_lists * kList;
@@ -125,74 +150,106 @@ select_kernel(SelectArgs a) {
   B2K_PHASE(0);
   load_list_keys(lst, E, skey);
   B2K_PHASE(1);
+  int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
 
-  // b_k = k-th best approximate score over every list; 0: fewer than k rows listed -> everything
-  // listed is a candidate.
-  block_topk_u64(skey, E, a.k, wtop, top);
-  B2K_PHASE(2);
-  const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
-  float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
-  // lower bound of the exact k-th best score: the k best approximate rows have exact >= b_k - eps
-  float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
+  if (a.k <= kList) {
+    // b_k = k-th best approximate score over every list; 0: fewer than k rows listed -> everything
+    // listed is a candidate.
+    block_topk_u64(skey, E, a.k, wtop, top);
+    B2K_PHASE(2);
+    const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
+    float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
+    // lower bound of the exact k-th best score: the k best approximate rows have exact >= b_k - eps
+    float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
+    if (bk != 0u && a.db_f32 != nullptr) tighten_threshold(a, q, lst, E, top, s_exact32, thr, lb);
 
-  // Tightening: the k rows with the best approximate scores are k distinct rows, so the smallest of
-  // their EXACT scores s' is a lower bound of the exact k-th best score, and every row of the exact
-  // top-k has b >= s' - eps.  s' >= b_k - eps, so this threshold is never looser than b_k - 2 eps and
-  // typically one eps tighter: several times fewer rows to re-rank.  (Spec R arithmetic.)
-  if (bk != 0u && a.db_f32 != nullptr) {
-    __shared__ float s_exact[B2K_MAX_K];
-    const float* qv = a.q + (int64_t)q * a.D;
-    for (int j = warp; j < a.k; j += (kSelThreads >> 5)) {
-      const int e = E - 1 - (int)(uint32_t)(top[j] & 0xffffffffull);
-      const float* x = a.db_f32 + (int64_t)lst[e].row * a.D;
-      const double p = lane_dot64(qv, x, a.D, lane);
-      const float sj = (float)warp_sum_f64(p);
-      if (lane == 0) s_exact[j] = sj;
+    B2K_PHASE(3);
+    // candidates + saturation, from the shared-memory keys (rows are fetched for hits only).
+    // Warp w owns lists w, w+8, ...; lane j = entry j of the list.
+    const uint32_t thr_key = float_key(thr);              // score >= thr  <=>  key >= thr_key
+    for (int l = warp; l < a.n_lists; l += (kSelThreads >> 5)) {
+      const uint64_t key = skey[l * kList + lane];
+      const uint32_t sk = (uint32_t)(key >> 32);
+      const bool hit = sk != 0u && sk >= thr_key;
+      const unsigned hm = __ballot_sync(0xffffffffu, hit);
+      // a list whose 32 slots are all at-risk rows may hide a 33rd: K-collect re-scans that DB split
+      // for this query and lists EVERY row at or above the threshold (so nothing is emitted here);
+      // only when the pair table is full does the query fall back to the exhaustive scan
+      if (hm == 0xffffffffu) {
+        if (lane == 0) {
+          const int slot = a.sat_pairs ? atomicAdd(a.sat_count, 1) : a.sat_cap;
+          if (slot < a.sat_cap) a.sat_pairs[slot] = make_int2(q, l);
+          else s_sat = 1;
+        }
+        if (a.sat_pairs) continue;     // on pair-table overflow the query is flagged: its candidates are unused
+      }
+      if (hm) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_count, __popc(hm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) {
+          const int pos = base + __popc(hm & ((1u << lane) - 1u));
+          if (pos < a.cand_cap) out_rows[pos] = lst[l * kList + lane].row;
+        }
+      }
     }
     __syncthreads();
-    float smin = INFINITY;
-    for (int j = 0; j < a.k; ++j) smin = fminf(smin, s_exact[j]);
-    const float t2 = __fsub_rd(smin, a.eps[q]);
-    if (t2 > thr) { thr = t2; lb = smin; }      // NaN-safe: keeps the looser bound
+    B2K_PHASE(4);
+    if (tid == 0) {
+      int cnt = s_count;
+      int flag = 0;
+      if (s_sat) flag |= 1;                       // a list may hide at-risk rows
+      if (cnt > a.cand_cap) { flag |= 2; cnt = a.cand_cap; }
+      if (a.force_exact) flag |= 4;
+      a.cand_count[q] = cnt;
+      a.flags[q] = flag;
+      a.thr[q] = thr;
+      a.lb[q] = lb;
+    }
+    return;
   }
 
-  B2K_PHASE(3);
-  // candidates + saturation, from the shared-memory keys (rows are fetched for hits only).
-  // Warp w owns lists w, w+8, ...; lane j = entry j of the list.
-  const uint32_t thr_key = float_key(thr);              // score >= thr  <=>  key >= thr_key
-  int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
-  for (int l = warp; l < a.n_lists; l += (kSelThreads >> 5)) {
-    const uint64_t key = skey[l * kList + lane];
+  // ---- k > 32: sort every listed entry; the candidates are a prefix of the sorted keys
+  int* l_cnt = reinterpret_cast<int*>(skey + P);                 // [n_lists] entries at or above the threshold
+  float* s_exact = reinterpret_cast<float*>(l_cnt + a.n_lists);  // [k]
+  for (int i = E + tid; i < P; i += kSelThreads) skey[i] = 0ull;
+  for (int l = tid; l < a.n_lists; l += kSelThreads) l_cnt[l] = 0;
+  __syncthreads();
+  block_bitonic_desc(skey, P);
+  const uint32_t bk = a.k <= E ? (uint32_t)(skey[a.k - 1] >> 32) : 0u;
+  float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
+  float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
+  if (bk != 0u && a.db_f32 != nullptr) tighten_threshold(a, q, lst, E, skey, s_exact, thr, lb);
+  const uint32_t thr_key = float_key(thr);
+  // pass 1: how many entries of each list reach the threshold (32 = saturated -> K-collect)
+  for (int i = tid; i < E; i += kSelThreads) {
+    const uint64_t key = skey[i];
     const uint32_t sk = (uint32_t)(key >> 32);
-    const bool hit = sk != 0u && sk >= thr_key;
-    const unsigned hm = __ballot_sync(0xffffffffu, hit);
-    // a list whose 32 slots are all at-risk rows may hide a 33rd: K-collect re-scans that DB split
-    // for this query and lists EVERY row at or above the threshold (so nothing is emitted here);
-    // only when the pair table is full does the query fall back to the exhaustive scan
-    if (hm == 0xffffffffu) {
-      if (lane == 0) {
-        const int slot = a.sat_pairs ? atomicAdd(a.sat_count, 1) : a.sat_cap;
-        if (slot < a.sat_cap) a.sat_pairs[slot] = make_int2(q, l);
-        else s_sat = 1;
-      }
-      if (a.sat_pairs) continue;     // on pair-table overflow the query is flagged: its candidates are unused
-    }
-    if (hm) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_count, __popc(hm));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (hit) {
-        const int pos = base + __popc(hm & ((1u << lane) - 1u));
-        if (pos < a.cand_cap) out_rows[pos] = lst[l * kList + lane].row;
-      }
-    }
+    if (sk != 0u && sk >= thr_key) atomicAdd(&l_cnt[(E - 1 - (int)(uint32_t)(key & 0xffffffffull)) / kList], 1);
   }
   __syncthreads();
-  B2K_PHASE(4);
+  for (int l = tid; l < a.n_lists; l += kSelThreads) {
+    if (l_cnt[l] == kList) {
+      const int slot = a.sat_pairs ? atomicAdd(a.sat_count, 1) : a.sat_cap;
+      if (slot < a.sat_cap) a.sat_pairs[slot] = make_int2(q, l);
+      else s_sat = 1;
+    }
+  }
+  // pass 2: emit the entries of the unsaturated lists
+  for (int i = tid; i < E; i += kSelThreads) {
+    const uint64_t key = skey[i];
+    const uint32_t sk = (uint32_t)(key >> 32);
+    if (sk == 0u || sk < thr_key) continue;
+    const int e = E - 1 - (int)(uint32_t)(key & 0xffffffffull);
+    if (l_cnt[e / kList] == kList && a.sat_pairs) continue;
+    const int pos = atomicAdd(&s_count, 1);
+    if (pos < a.cand_cap) out_rows[pos] = lst[e].row;
+  }
+  __syncthreads();
   if (tid == 0) {
     int cnt = s_count;
     int flag = 0;
-    if (s_sat) flag |= 1;                       // a list may hide at-risk rows
+    if (s_sat) flag |= 1;
     if (cnt > a.cand_cap) { flag |= 2; cnt = a.cand_cap; }
     if (a.force_exact) flag |= 4;
     a.cand_count[q] = cnt;
@@ -204,15 +261,23 @@ select_kernel(SelectArgs a) {
 
 // One CTA per query: admission floor for the full pass from the lists of the sampling pass.
 __global__ void __launch_bounds__(kSelThreads)
-seed_kernel(SeedArgs a) {
+seed_kernel(SeedArgs a, int P) {
   extern __shared__ uint64_t skey[];
   __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
-  __shared__ uint64_t top[B2K_MAX_K];
+  __shared__ uint64_t top[kList];
   const int q = blockIdx.x;
   const int E = a.n_lists * kList;
   load_list_keys(a.partial + (int64_t)q * a.list_stride * kList, E, skey);
-  block_topk_u64(skey, E, a.k, wtop, top);
-  const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
+  uint32_t bk;
+  if (a.k <= kList) {
+    block_topk_u64(skey, E, a.k, wtop, top);
+    bk = (uint32_t)(top[a.k - 1] >> 32);
+  } else {
+    for (int i = E + threadIdx.x; i < P; i += kSelThreads) skey[i] = 0ull;
+    __syncthreads();
+    block_bitonic_desc(skey, P);
+    bk = a.k <= E ? (uint32_t)(skey[a.k - 1] >> 32) : 0u;
+  }
   if (threadIdx.x == 0) {
     // strictly below b_k(sample) - 2 eps <= b_k(shard) - 2 eps: rows at or under the floor are
     // never candidates, and rows above it are admitted (strict compare in the scoring epilogue)
@@ -240,12 +305,13 @@ rerank_kernel(RerankArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// One CTA per query: top-k of the re-ranked candidates.  Dynamic smem: cand_cap u64 keys.
+// One CTA per query: top-k of the re-ranked candidates.  Dynamic smem: cand_cap u64 keys (k <= 32) or
+// P >= cand_cap keys sorted in place (k > 32).
 __global__ void __launch_bounds__(kSelThreads)
-finalize_kernel(FinalizeArgs a) {
+finalize_kernel(FinalizeArgs a, int P) {
   extern __shared__ uint64_t fkeys[];
   __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
-  __shared__ uint64_t top[B2K_MAX_K];
+  __shared__ uint64_t top[kList];
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const int flag = a.flags[q];
@@ -259,11 +325,18 @@ finalize_kernel(FinalizeArgs a) {
   const int cnt = min(a.cand_count[q], a.cand_cap);
   for (int c = tid; c < cnt; c += kSelThreads)
     fkeys[c] = cand_key(a.cand_ip[(int64_t)q * a.cand_cap + c], a.cand_rows[(int64_t)q * a.cand_cap + c]);
-  __syncthreads();
-  block_topk_u64(fkeys, cnt, a.k, wtop, top);
-  if (tid < a.k) {
-    const int j = tid;
-    const uint64_t best = top[j];
+  const uint64_t* best_keys = top;
+  if (a.k <= kList) {
+    __syncthreads();
+    block_topk_u64(fkeys, cnt, a.k, wtop, top);
+  } else {
+    for (int c = cnt + tid; c < P; c += kSelThreads) fkeys[c] = 0ull;
+    __syncthreads();
+    block_bitonic_desc(fkeys, P);
+    best_keys = fkeys;
+  }
+  for (int j = tid; j < a.k; j += kSelThreads) {
+    const uint64_t best = j < P || a.k <= kList ? best_keys[j] : 0ull;
     float ip = -3.402823466e38f, dist = 3.402823466e38f;
     int64_t lab = -1;
     if (best != 0ull) {
@@ -279,7 +352,19 @@ finalize_kernel(FinalizeArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// One warp per query; n_lists*k <= 32*32 entries.  Order: higher ip, then lower offset.
+// One warp per query, n_lists <= 32 lists in the global order (what K-finalize / K-exact emit).
+__global__ void __launch_bounds__(128)
+merge_sorted_kernel(MergeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= a.nq) return;
+  const int64_t nq = a.nq, k = a.k;
+  warp_merge_sorted(a.ip, a.dist, a.labels, [=](int g, int j) { return ((int64_t)g * nq + q) * k + j; }, a.n_lists, a.k, lane,
+                    a.out_ip ? a.out_ip + (int64_t)q * a.k : nullptr, a.out_dist + (int64_t)q * a.k,
+                    a.out_labels + (int64_t)q * a.k);
+}
+
+// One warp per query; any order inside the lists, n_lists*k <= 32*32 entries (more than 32 lists).
 __global__ void __launch_bounds__(128)
 merge_kernel(MergeArgs a) {
   const int lane = threadIdx.x & 31;
@@ -324,21 +409,29 @@ merge_kernel(MergeArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+static int pow2_at_least(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
 int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
-  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint64_t);
-  if (smem > 200 * 1024) { set_error("select: too many partial lists (%d)", a.n_lists); return B2K_E_INVALID; }
+  const int E = a.n_lists * kList;
+  const int P = a.k <= kList ? 0 : pow2_at_least(E);
+  const size_t smem = a.k <= kList ? (size_t)E * sizeof(uint64_t)
+                                   : (size_t)P * sizeof(uint64_t) + (size_t)a.n_lists * sizeof(int) + (size_t)a.k * sizeof(float);
+  if (smem > 200 * 1024) { set_error("select: too many partial lists (%d) for k=%d", a.n_lists, a.k); return B2K_E_INVALID; }
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  select_kernel<<<nq, kSelThreads, smem, st>>>(a);
+  select_kernel<<<nq, kSelThreads, smem, st>>>(a, P);
   B2K_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_seed(const SeedArgs& a, int nq, cudaStream_t st) {
-  const size_t smem = (size_t)a.n_lists * kList * sizeof(uint64_t);
+  const int E = a.n_lists * kList;
+  const int P = a.k <= kList ? 0 : pow2_at_least(E);
+  const size_t smem = (size_t)(a.k <= kList ? E : P) * sizeof(uint64_t);
+  if (smem > 200 * 1024) { set_error("seed: too many partial lists (%d)", a.n_lists); return B2K_E_INVALID; }
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  seed_kernel<<<nq, kSelThreads, smem, st>>>(a);
+  seed_kernel<<<nq, kSelThreads, smem, st>>>(a, P);
   B2K_CHECK_LAUNCH();
   return 0;
 }
@@ -354,17 +447,20 @@ int launch_rerank(const RerankArgs& a, int n_sm, cudaStream_t st) {
 }
 
 int launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)a.cand_cap * sizeof(uint64_t);
+  const int P = a.k <= kList ? 0 : pow2_at_least(a.cand_cap);
+  const size_t smem = (size_t)(a.k <= kList ? a.cand_cap : P) * sizeof(uint64_t);
+  if (smem > 200 * 1024) { set_error("finalize: %d candidate slots do not fit shared memory", a.cand_cap); return B2K_E_INVALID; }
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  finalize_kernel<<<a.nq, kSelThreads, smem, st>>>(a);
+  finalize_kernel<<<a.nq, kSelThreads, smem, st>>>(a, P);
   B2K_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_merge(const MergeArgs& a, cudaStream_t st) {
   if (a.nq <= 0) return 0;
-  merge_kernel<<<(a.nq + 3) / 4, 128, 0, st>>>(a);
+  if (a.n_lists <= 32) merge_sorted_kernel<<<(a.nq + 3) / 4, 128, 0, st>>>(a);
+  else merge_kernel<<<(a.nq + 3) / 4, 128, 0, st>>>(a);
   B2K_CHECK_LAUNCH();
   return 0;
 }

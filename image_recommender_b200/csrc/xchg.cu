@@ -82,40 +82,9 @@ xchg_merge_kernel(const unsigned char* __restrict__ mine, XchgLayout lay, int pa
   const float* ip = reinterpret_cast<const float*>(mine + lay.ip_off(parity, 0));
   const float* dist = reinterpret_cast<const float*>(mine + lay.dist_off(parity, 0));
   const int64_t* lab = reinterpret_cast<const int64_t*>(mine + lay.lab_off(parity, 0));
-  const int E = lay.world * k;
-  uint32_t last_key = 0xffffffffu;
-  int64_t last_off = -1;
-  for (int j = 0; j < k; ++j) {
-    uint32_t bk = 0u; int64_t bo = INT64_MAX; int64_t bsrc = -1;
-    for (int e = lane; e < E; e += 32) {
-      const int g = e / k, jj = e % k;
-      const int64_t src = (int64_t)g * lay.cap + (int64_t)q * k + jj;
-      const int64_t off = lab[src];
-      if (off < 0) continue;
-      const uint32_t key = float_key(ip[src]);
-      const bool remaining = (j == 0) || key < last_key || (key == last_key && off > last_off);
-      if (!remaining) continue;
-      if (bsrc < 0 || key > bk || (key == bk && off < bo)) { bk = key; bo = off; bsrc = src; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int64_t oo = __shfl_xor_sync(0xffffffffu, bo, o);
-      const int64_t os = __shfl_xor_sync(0xffffffffu, bsrc, o);
-      const bool take = os >= 0 && (bsrc < 0 || ok > bk || (ok == bk && oo < bo));
-      if (take) { bk = ok; bo = oo; bsrc = os; }
-    }
-    if (lane == 0) {
-      float o_ip = -3.402823466e38f, o_d = 3.402823466e38f;
-      int64_t o_l = -1;
-      if (bsrc >= 0) { o_ip = ip[bsrc]; o_d = dist[bsrc]; o_l = bo; }
-      if (out_ip) out_ip[(int64_t)q * k + j] = o_ip;
-      out_dist[(int64_t)q * k + j] = o_d;
-      out_labels[(int64_t)q * k + j] = o_l;
-    }
-    if (bsrc < 0) { last_key = 0u; last_off = INT64_MAX; }
-    else { last_key = bk; last_off = bo; }
-  }
+  const int64_t cap = lay.cap;
+  warp_merge_sorted(ip, dist, lab, [=](int g, int j) { return (int64_t)g * cap + (int64_t)q * k + j; }, lay.world, k, lane,
+                    out_ip ? out_ip + (int64_t)q * k : nullptr, out_dist + (int64_t)q * k, out_labels + (int64_t)q * k);
 }
 
 }  // namespace b2k

@@ -28,6 +28,7 @@ class PeerExchange:
         self._C, self._capi = C, _capi
         self._lib = _capi.load_library()
         self.device, self.rank, self.world = device, rank, world
+        self.max_entries = int(max_entries)
         h = C.c_void_p()
         _capi.check(self._lib.b2k_xchg_create(device, rank, world, max_entries, C.byref(h)))
         self._h = h
@@ -117,7 +118,7 @@ class ShardedSearcher:
         self.local_search(q, k, (dist_t, lab, ip_t))
         if self.world == 1:
             return dist_t, lab, ip_t
-        if self.exchange is not None:
+        if self.exchange is not None and nq * k <= self.exchange.max_entries:
             if self._out is None or self._out[0].shape != (nq, k):
                 self._out = (torch.empty((nq, k), dtype=torch.float32, device=q.device),
                              torch.empty((nq, k), dtype=torch.int64, device=q.device),
@@ -159,8 +160,9 @@ class ShardedIndex:
         shard = FlatShard.load(path, device=device, row_begin=r0, row_end=r1)
         exchange = None
         if world > 1 and peer:
-            from ._capi import B2K_MAX_K
-            exchange = PeerExchange(device, rank, world, max_entries=max_batch * B2K_MAX_K, group=group)
+            from ._capi import B2K_LIST
+            # sized for the tuned case k <= 32; larger nq * k falls back to the all-gather path
+            exchange = PeerExchange(device, rank, world, max_entries=max_batch * B2K_LIST, group=group)
         out = cls(shard, info["n_rows"], group=group, exchange=exchange)
         out._max_batch = max_batch
         return out

@@ -25,7 +25,8 @@ extern "C" {
 
 #define B2K_ABI_VERSION 1
 #define B2K_MAX_TABLES 8
-#define B2K_MAX_K 32          /* top-k limit of the fused selection (list width per DB split) */
+#define B2K_MAX_K 1024        /* top-k limit.  k <= 32 is the tuned case; above it the engine uses more DB  */
+                              /* splits and sorts the per-query lists instead of extracting k items         */
 #define B2K_LIST 32           /* entries kept per (query, DB split) by the scoring kernels   */
 
 #define B2K_E_INVALID  (-1)   /* bad argument                                   */
@@ -153,7 +154,9 @@ int b2k_get_stats(b2k_index* idx, b2k_stats* out);   /* synchronises the last se
 int b2k_set_option(b2k_index* idx, int32_t key, int64_t value);
 
 /* Cross-shard merge (new): n_lists per-shard results [n_lists, nq, k] ->
- * [nq, k], order = higher ip first, then lower offset.  All pointers on `device`. */
+ * [nq, k], order = higher ip first, then lower offset.  All pointers on `device`.  Up to 32 lists
+ * (any k): every list must already be in that order with its -1 padding last, which is what
+ * b2k_search* returns; more lists: any order, n_lists * k <= 1024. */
 int b2k_merge_topk_device(const float* ip, const float* dist, const int64_t* labels,
                           int32_t n_lists, int32_t nq, int32_t k,
                           float* out_ip, float* out_dist, int64_t* out_labels,

@@ -177,6 +177,67 @@ def test_threshold_tightening_keeps_bits_and_cuts_candidates_tc(db20k):
     assert cands[("tc2", 1)] >= 10
 
 
+@pytest.mark.parametrize("path", ["scan", "tc", "tc2"])
+@pytest.mark.parametrize("nq,k", [(1, 33), (5, 100), (130, 64), (300, 500), (3, 1024)])
+def test_large_k_matches_oracle(db20k, path, nq, k):
+    """k > 32 (faiss accepts any k): more DB splits, sorted per-query lists, paged exhaustive scan —
+    same bits as the oracle on every path, certified or not."""
+    from image_recommender_b200 import _capi
+    ix, pk, n = db20k
+    want = _set_path(ix, path)
+    if path == "scan" and nq > 8:
+        pytest.skip("K-scan serves tiny batches")
+    q = oracle.synth_queries(DIMS, nq, n, n_clusters=8, qseed=500 + k)
+    st = _check(ix, pk, q, k)
+    assert st["path"] == want
+    if k in (33, 100):
+        ix.set_option(_capi.OPT_FORCE_EXACT, 1)           # the paged exhaustive scan alone
+        st = _check(ix, pk, q, k)
+        assert st["n_uncertified"] == nq
+        ix.set_option(_capi.OPT_FORCE_EXACT, 0)
+    _set_path(ix, "auto")
+
+
+def test_large_k_edge_cases(gpu):
+    """k beyond the row count (padding), beyond the limit (error), ties across a page boundary of the
+    exhaustive scan, and a cross-shard merge of k = 100 lists."""
+    import torch
+    irb = _irb()
+    from image_recommender_b200 import _capi
+    tabs, _ = _mk(700)
+    for t in tabs:
+        t[200:290] = t[5]                  # 91 identical rows: exact ties straddle results 32 / 64
+    pk = oracle.pack(tabs)
+    ix = irb.FlatShard(DIMS, 700, device=gpu)
+    ix.add_tables(tabs)
+    q = oracle.normalize_l2(pk["f32"][[5, 250, 17]])
+    for path in ("scan", "tc", "tc2"):
+        _set_path(ix, path)
+        for force in (0, 1):
+            ix.set_option(_capi.OPT_FORCE_EXACT, force)
+            _check(ix, pk, q, 100)
+            dist, lab, ip = ix.search_ip(q, 1000)         # k > ntotal: -1 padding after 700 results
+            assert (lab[:, 700:] == -1).all() and (lab[:, :700] >= 0).all()
+            _check(ix, pk, q, 1000)
+    ix.set_option(_capi.OPT_FORCE_EXACT, 0)
+    with pytest.raises(irb.B2KError):
+        ix.search(q, 1025)
+    # two shards, k = 100, merged on the device
+    a = irb.FlatShard(DIMS, 300, device=gpu, base_offset=0)
+    b = irb.FlatShard(DIMS, 400, device=gpu, base_offset=300)
+    a.add_tables([t[:300] for t in tabs]); b.add_tables([t[300:] for t in tabs])
+    qd = torch.from_numpy(q).cuda(gpu)
+    ra, rb = a.search_device(qd, 100), b.search_device(qd, 100)
+    m_dist, m_lab, m_ip = irb.merge_topk_device(torch.stack([ra[2], rb[2]]).contiguous(), torch.stack([ra[0], rb[0]]).contiguous(),
+                                                torch.stack([ra[1], rb[1]]).contiguous())
+    torch.cuda.synchronize()
+    w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q, 100, pk["norm2"])
+    assert np.array_equal(m_lab.cpu().numpy(), w_lab)
+    assert np.array_equal(m_ip.cpu().numpy().view(np.uint32), w_ip.view(np.uint32))
+    assert np.array_equal(m_dist.cpu().numpy().view(np.uint32), w_dist.view(np.uint32))
+    ix.close(); a.close(); b.close()
+
+
 def test_search_auto_path_and_fallback_tc(db20k):
     from image_recommender_b200 import _capi
     ix, pk, n = db20k
@@ -300,7 +361,7 @@ def test_near_duplicate_runs_are_collected(gpu, path):
     ix.close()
 
 
-@pytest.mark.parametrize("dims,n", [([32768], 700), ([4096, 64], 1500), ([128], 5000)])
+@pytest.mark.parametrize("dims,n", [([32768], 700), ([4096, 64], 1500), ([128], 5000), ([5, 3, 70], 3000), ([1], 500)])
 def test_other_baseline_dims_match_oracle(gpu, dims, n):
     """BASELINE configs 4 / 4s: the raw 32768-d SIFT-VLAD descriptor, a wide two-table combo, and the
     stored 128-d table.  Pack, batch-1 and batch-130 search bit-equal to the oracle."""
