@@ -154,3 +154,62 @@ def test_native_ingest_declines_foreign_blob_and_python_takes_over(tmp_path, gpu
     assert any("Native ingest declined" in m for m in log_nat)
     assert len(tab_nat) == 700 and tab_nat == tab_py
     assert f_nat.read_bytes() == f_py.read_bytes()
+
+
+# ------------------------------------------------------------------------------- property tests (CPU)
+def test_blob_recogniser_never_misreads_mutated_blobs():
+    """Fuzz: random byte edits / truncations of valid blobs.  Whatever the recogniser accepts must be
+    exactly what the unpickler (the reference's decoder) yields for the same bytes — it may decline
+    anything, it may never invent floats — and it must not read outside the buffer (no crash)."""
+    from hypothesis import given, settings, strategies as st
+    import image_recommender_b200 as irb
+
+    base = [_dump(np.random.default_rng(i).standard_normal(d).astype(np.float32)) for i, d in enumerate((1, 7, 48, 128, 300))]
+
+    @settings(max_examples=400, deadline=None)
+    @given(which=st.integers(0, len(base) - 1), edits=st.lists(st.tuples(st.integers(0, 1 << 30), st.integers(0, 255)), max_size=4),
+           cut=st.one_of(st.none(), st.integers(0, 1 << 30)))
+    def run(which, edits, cut):
+        b = bytearray(base[which])
+        for pos, val in edits:
+            b[pos % len(b)] = val
+        if cut is not None:
+            b = b[:cut % (len(b) + 1)]
+        blob = bytes(b)
+        got = irb.parse_f32_blob(blob)
+        if got is None:
+            return
+        try:
+            want = pickle.loads(blob)
+        except Exception:
+            want = None
+        if isinstance(want, np.ndarray) and want.dtype == np.float32 and want.ndim == 1:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        else:
+            # accepted although the unpickler disagrees: only tolerable when the edit hit pickle
+            # framing/memo bytes the recogniser does not interpret, never the payload length or dtype
+            head = blob.index(b"(\x96")
+            n_bytes = int.from_bytes(blob[head + 2:head + 10], "little")
+            assert got.size * 4 == n_bytes and blob[head + 10:head + 10 + n_bytes] == got.tobytes()
+
+    run()
+
+
+def test_shard_ranges_partition_the_rows():
+    """shard_range(): contiguous, ordered, disjoint ranges covering [0, n) exactly — the property that
+    makes global offset = base + local row (create_index.py:236-249) hold on any number of GPUs."""
+    from hypothesis import given, settings, strategies as st
+    from image_recommender_b200.sharded import shard_range
+
+    @settings(max_examples=300, deadline=None)
+    @given(n=st.integers(0, 10 ** 9), world=st.integers(1, 64))
+    def run(n, world):
+        edges = [shard_range(n, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+            assert a0 <= a1 == b0 <= b1
+        sizes = [b - a for a, b in edges]
+        assert sizes == sorted(sizes, reverse=True)               # ceil(n/world) rows each, only tail shards shorter
+        assert max(sizes) == -(-n // world)
+
+    run()
