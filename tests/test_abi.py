@@ -70,3 +70,37 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "image_recommender_b200" / "csrc").glob("*"):
         assert "oracle/" not in p.read_text().replace("oracle/b2k_oracle.c follows", "").replace(
             "(oracle/b2k_oracle.c", "(").replace("oracle/synth.py", "") or True
+
+
+def _build_c_demo(tmp_path):
+    import subprocess
+    exe = tmp_path / "c_abi_demo"
+    lib = ROOT / "image_recommender_b200" / "libb2k.so"
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-std=c99", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "c_abi_demo.c"),
+                        "-o", str(exe), str(lib), "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe, {"LD_LIBRARY_PATH": str(lib.parent)}
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/b2k.h compiles as C99 and a C client links against libb2k.so (no torch / Python types at
+    the boundary); without a GPU the client stops at b2k_device_count."""
+    import os
+    import subprocess
+    import image_recommender_b200 as irb
+    exe, env = _build_c_demo(tmp_path)
+    if irb.device_count() > 0:
+        pytest.skip("a GPU is visible: the gpu-marked twin runs the client")
+    r = subprocess.run([str(exe), "100", "2", "5"], env={**os.environ, **env}, capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_client_end_to_end(tmp_path):
+    """examples/c_abi_demo.c: add in two batches, search, brute-force check in C, save/load round trip."""
+    import os
+    import subprocess
+    exe, env = _build_c_demo(tmp_path)
+    for args in (["20000", "9", "10"], ["3000", "130", "5"], ["5000", "3", "40"]):
+        r = subprocess.run([str(exe), *args], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr)
