@@ -143,6 +143,35 @@ __device__ __forceinline__ double lane_dot64(const float* __restrict__ q, const 
   return p;
 }
 
+// Same arithmetic with the query already widened to fp64 (shared memory): one fp32->fp64 conversion per
+// element instead of two — the conversion rate (16/clk/SM), not HBM, bounds a throughput-bound re-rank.
+__device__ __forceinline__ double lane_dot64_qd(const double* __restrict__ qd, const float* __restrict__ x, int d, int lane) {
+  double p = 0.0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const int n4 = d >> 2;
+  int i = lane;
+  for (; i + 7 * 32 < n4; i += 8 * 32) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(x4 + i + u * 32);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double2 w01 = *reinterpret_cast<const double2*>(qd + 4 * (i + u * 32));
+      const double2 w23 = *reinterpret_cast<const double2*>(qd + 4 * (i + u * 32) + 2);
+      p = __fma_rn(w01.x, (double)v[u].x, p); p = __fma_rn(w01.y, (double)v[u].y, p);
+      p = __fma_rn(w23.x, (double)v[u].z, p); p = __fma_rn(w23.y, (double)v[u].w, p);
+    }
+  }
+  for (; i < n4; i += 32) {
+    const float4 v = __ldg(x4 + i);
+    const double2 w01 = *reinterpret_cast<const double2*>(qd + 4 * i);
+    const double2 w23 = *reinterpret_cast<const double2*>(qd + 4 * i + 2);
+    p = __fma_rn(w01.x, (double)v.x, p); p = __fma_rn(w01.y, (double)v.y, p);
+    p = __fma_rn(w23.x, (double)v.z, p); p = __fma_rn(w23.y, (double)v.w, p);
+  }
+  return p;
+}
+
 // G-way merge (G <= 32) of per-shard result lists, each already in the global order (higher ip, then
 // lower offset) with label < 0 padding at its end: one warp per query, lane g walks list g, every
 // step is one warp arg-best.  O(k log G) for any k.  addr(g, j) = flat index of entry j of list g.

@@ -326,11 +326,32 @@ int launch_collect(const CollectArgs& a, int n_sm, cudaStream_t st) {
 namespace {
 constexpr int kExactFQ = 4;
 constexpr int kExactWarps = 8;
+constexpr int kExactRows = 4;       // rows per warp step of the staged-query form
 
 }  // namespace
 
+// Offer (ip, row) to the warp's register-resident top-32 of failed query f (one entry per lane).
+__device__ __forceinline__ void exact_offer(float ip, int64_t row, uint64_t ceil_key, float& e_s, int32_t& e_r,
+                                            float& tau, int lane) {
+  if (ip > tau && cand_key(ip, (int32_t)row) < ceil_key) {   // equal scores: the earlier (lower) row already listed wins
+    const uint64_t k = cand_key(e_s, e_r);
+    const uint64_t kmin = warp_min_u64(k);
+    const unsigned vm = __ballot_sync(0xffffffffu, k == kmin);
+    if (lane == __ffs(vm) - 1) { e_s = ip; e_r = (int32_t)row; }
+    float sc = e_r < 0 ? -INFINITY : e_s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sc = fminf(sc, __shfl_xor_sync(0xffffffffu, sc, o));
+    tau = sc;
+  }
+}
+
+// q_smem: the (<= 4) failed queries are staged as fp64 in dynamic shared memory and every warp step
+// takes kExactRows rows, so each row element costs ONE fp32->fp64 conversion (the 16/clk/SM
+// conversion rate, not HBM, bounded the one-row-at-a-time form) and each staged query chunk serves
+// four rows.  The FMA order per lane is Spec R's in both forms.
 __global__ void __launch_bounds__(kExactWarps * 32)
-exact_scan_kernel(ExactArgs a) {
+exact_scan_kernel(ExactArgs a, int q_smem) {
+  extern __shared__ double qd[];                                    // [kExactFQ][D] when q_smem
   __shared__ uint64_t keys[kExactFQ][kExactWarps * 32];
   const int n_fail = *a.fail_count;
   if (n_fail == 0) return;
@@ -349,49 +370,88 @@ exact_scan_kernel(ExactArgs a) {
       e_s[f] = -INFINITY; e_r[f] = -1; tau[f] = -INFINITY;
       ceil_key[f] = a.page == 0 ? ~0ull : a.ceil_keys[fi];
     }
-    for (int64_t row = gw; row < a.n_rows; row += nw) {
-      const float* x = a.db_f32 + row * (int64_t)a.D;
-      double p[kExactFQ];
+    if (q_smem) {
+      __syncthreads();                                              // previous group's readers are done
 #pragma unroll
-      for (int f = 0; f < kExactFQ; ++f) p[f] = 0.0;
-      if (vec) {
-        const float4* x4 = reinterpret_cast<const float4*>(x);
-        for (int c = lane; c < (a.D >> 2); c += 32) {
-          const float4 v = x4[c];
+      for (int f = 0; f < kExactFQ; ++f)
+        for (int i = threadIdx.x; i < a.D; i += blockDim.x) qd[(size_t)f * a.D + i] = (double)__ldg(qp[f] + i);
+      __syncthreads();
+      const int n4 = a.D >> 2;
+      for (int64_t row0 = gw * kExactRows; row0 < a.n_rows; row0 += nw * kExactRows) {
+        const float4* x4[kExactRows];
+#pragma unroll
+        for (int r = 0; r < kExactRows; ++r)                        // rows past the end re-read the last row, unused
+          x4[r] = reinterpret_cast<const float4*>(a.db_f32 + min(row0 + r, a.n_rows - 1) * (int64_t)a.D);
+        double p[kExactRows][kExactFQ];
+#pragma unroll
+        for (int r = 0; r < kExactRows; ++r)
+#pragma unroll
+          for (int f = 0; f < kExactFQ; ++f) p[r][f] = 0.0;
+        float4 nxt[kExactRows];
+#pragma unroll
+        for (int r = 0; r < kExactRows; ++r) nxt[r] = lane < n4 ? __ldcs(x4[r] + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = lane; c < n4; c += 32) {
+          double xv[kExactRows][4];
+#pragma unroll
+          for (int r = 0; r < kExactRows; ++r) {
+            xv[r][0] = (double)nxt[r].x; xv[r][1] = (double)nxt[r].y; xv[r][2] = (double)nxt[r].z; xv[r][3] = (double)nxt[r].w;
+          }
+          if (c + 32 < n4) {                                        // next chunk's loads fly during this chunk's FMAs
+#pragma unroll
+            for (int r = 0; r < kExactRows; ++r) nxt[r] = __ldcs(x4[r] + c + 32);
+          }
 #pragma unroll
           for (int f = 0; f < kExactFQ; ++f) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(qp[f]) + c);
-            p[f] = __fma_rn((double)w.x, (double)v.x, p[f]);
-            p[f] = __fma_rn((double)w.y, (double)v.y, p[f]);
-            p[f] = __fma_rn((double)w.z, (double)v.z, p[f]);
-            p[f] = __fma_rn((double)w.w, (double)v.w, p[f]);
-          }
-        }
-      } else {
-        for (int c = lane; c * 4 < a.D; c += 32)
-          for (int j = 0; j < 4; ++j) {
-            const int i = c * 4 + j;
-            if (i < a.D) {
-              const double v = (double)x[i];
+            const double2 w01 = *reinterpret_cast<const double2*>(qd + (size_t)f * a.D + 4 * c);
+            const double2 w23 = *reinterpret_cast<const double2*>(qd + (size_t)f * a.D + 4 * c + 2);
 #pragma unroll
-              for (int f = 0; f < kExactFQ; ++f) p[f] = __fma_rn((double)__ldg(qp[f] + i), v, p[f]);
+            for (int r = 0; r < kExactRows; ++r) {
+              p[r][f] = __fma_rn(w01.x, xv[r][0], p[r][f]); p[r][f] = __fma_rn(w01.y, xv[r][1], p[r][f]);
+              p[r][f] = __fma_rn(w23.x, xv[r][2], p[r][f]); p[r][f] = __fma_rn(w23.y, xv[r][3], p[r][f]);
             }
           }
-      }
-#pragma unroll
-      for (int f = 0; f < kExactFQ; ++f) {
-        const float ip = (float)warp_sum_f64(p[f]);
-        if (ip > tau[f] && cand_key(ip, (int32_t)row) < ceil_key[f]) {   // equal scores: the earlier (lower) row already listed wins
-          // replace the warp list's minimum (lane-per-entry, in registers)
-          const uint64_t k = cand_key(e_s[f], e_r[f]);
-          const uint64_t kmin = warp_min_u64(k);
-          const unsigned vm = __ballot_sync(0xffffffffu, k == kmin);
-          if (lane == __ffs(vm) - 1) { e_s[f] = ip; e_r[f] = (int32_t)row; }
-          float sc = e_r[f] < 0 ? -INFINITY : e_s[f];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sc = fminf(sc, __shfl_xor_sync(0xffffffffu, sc, o));
-          tau[f] = sc;
         }
+#pragma unroll
+        for (int r = 0; r < kExactRows; ++r) {
+          if (row0 + r >= a.n_rows) break;                          // warp-uniform
+#pragma unroll
+          for (int f = 0; f < kExactFQ; ++f)
+            exact_offer((float)warp_sum_f64(p[r][f]), row0 + r, ceil_key[f], e_s[f], e_r[f], tau[f], lane);
+        }
+      }
+    } else {
+      for (int64_t row = gw; row < a.n_rows; row += nw) {
+        const float* x = a.db_f32 + row * (int64_t)a.D;
+        double p[kExactFQ];
+#pragma unroll
+        for (int f = 0; f < kExactFQ; ++f) p[f] = 0.0;
+        if (vec) {
+          const float4* x4 = reinterpret_cast<const float4*>(x);
+          for (int c = lane; c < (a.D >> 2); c += 32) {
+            const float4 v = x4[c];
+#pragma unroll
+            for (int f = 0; f < kExactFQ; ++f) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(qp[f]) + c);
+              p[f] = __fma_rn((double)w.x, (double)v.x, p[f]);
+              p[f] = __fma_rn((double)w.y, (double)v.y, p[f]);
+              p[f] = __fma_rn((double)w.z, (double)v.z, p[f]);
+              p[f] = __fma_rn((double)w.w, (double)v.w, p[f]);
+            }
+          }
+        } else {
+          for (int c = lane; c * 4 < a.D; c += 32)
+            for (int j = 0; j < 4; ++j) {
+              const int i = c * 4 + j;
+              if (i < a.D) {
+                const double v = (double)x[i];
+#pragma unroll
+                for (int f = 0; f < kExactFQ; ++f) p[f] = __fma_rn((double)__ldg(qp[f] + i), v, p[f]);
+              }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < kExactFQ; ++f)
+          exact_offer((float)warp_sum_f64(p[f]), row, ceil_key[f], e_s[f], e_r[f], tau[f], lane);
       }
     }
     // CTA merge of the 8 warp lists -> top-32 per failed query
@@ -450,7 +510,12 @@ exact_finalize_kernel(ExactArgs a, int P) {
 int exact_num_splits(int n_sm) { return 2 * n_sm; }
 
 int launch_exact(const ExactArgs& a, cudaStream_t st) {
-  exact_scan_kernel<<<a.n_splits, kExactWarps * 32, 0, st>>>(a);
+  // staged fp64 queries need 4 x D x 8 bytes of shared memory, 16-byte aligned fp32 rows and D % 4 == 0
+  const size_t q_bytes = (size_t)kExactFQ * a.D * sizeof(double);
+  const int q_smem = (a.D & 3) == 0 && q_bytes <= 160 * 1024 && (reinterpret_cast<uintptr_t>(a.db_f32) & 15) == 0;
+  if (q_smem && q_bytes > 32 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_bytes));
+  exact_scan_kernel<<<a.n_splits, kExactWarps * 32, q_smem ? q_bytes : 0, st>>>(a, q_smem);
   B2K_CHECK_LAUNCH();
   int P = 1; while (P < a.n_splits * kList) P <<= 1;
   const size_t smem = (size_t)P * 8;

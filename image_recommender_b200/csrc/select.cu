@@ -288,17 +288,24 @@ seed_kernel(SeedArgs a, int P) {
 // ---------------------------------------------------------------------------------------
 // grid = (blocks_per_query, nq); warp-per-candidate, Spec R.
 __global__ void __launch_bounds__(256)
-rerank_kernel(RerankArgs a) {
+rerank_kernel(RerankArgs a, int q_smem) {
+  extern __shared__ double qd[];          // [D] the query widened to fp64, when q_smem
   const int q = blockIdx.y;
   const int cnt = min(a.cand_count[q], a.cand_cap);    // K-collect may have counted past the capacity
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int w0 = blockIdx.x * wpb + (threadIdx.x >> 5);
   const int wstride = gridDim.x * wpb;
+  if (blockIdx.x * wpb >= cnt) return;                 // nothing for this block (uniform)
   const float* __restrict__ qv = a.q + (int64_t)q * a.D;
+  if (q_smem) {
+    for (int i = threadIdx.x; i < a.D; i += blockDim.x) qd[i] = (double)__ldg(qv + i);
+    __syncthreads();
+  }
   for (int c = w0; c < cnt; c += wstride) {
     const int32_t row = a.cand_rows[(int64_t)q * a.cand_cap + c];
-    const double p = lane_dot64(qv, a.db_f32 + (int64_t)row * a.D, a.D, lane);
+    const float* x = a.db_f32 + (int64_t)row * a.D;
+    const double p = q_smem ? lane_dot64_qd(qd, x, a.D, lane) : lane_dot64(qv, x, a.D, lane);
     const float ip = (float)warp_sum_f64(p);
     if (lane == 0) a.cand_ip[(int64_t)q * a.cand_cap + c] = ip;
   }
@@ -441,7 +448,14 @@ int launch_rerank(const RerankArgs& a, int n_sm, cudaStream_t st) {
   if (bpq < 1) bpq = 1;
   if (bpq > 128) bpq = 128;
   dim3 grid(bpq, a.nq);
-  rerank_kernel<<<grid, 256, 0, st>>>(a);
+  // one block serves many candidates of one query only when blocks are scarce (large batches): then the
+  // widened query in shared memory halves the conversions; small batches keep the latency-lean form
+  const size_t q_bytes = (size_t)a.D * sizeof(double);
+  const int q_smem = bpq == 1 && (a.D & 3) == 0 && q_bytes <= 96 * 1024 &&
+                     ((reinterpret_cast<uintptr_t>(a.db_f32) | reinterpret_cast<uintptr_t>(a.q)) & 15) == 0;
+  if (q_smem && q_bytes > 48 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_bytes));
+  rerank_kernel<<<grid, 256, q_smem ? q_bytes : 0, st>>>(a, q_smem);
   B2K_CHECK_LAUNCH();
   return 0;
 }
