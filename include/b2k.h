@@ -47,7 +47,7 @@ typedef struct b2k_index b2k_index;
                                  /* tcgen05 path measured faster at every batch size and row width)      */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
 #define B2K_OPT_TIGHTEN       8  /* candidate threshold from the exact scores of the k best rows: 1 auto (default: */
-                                 /* batches of 256 queries and more), 0 off, 2 always                           */
+                                 /* batches of 32 queries and more), 0 off, 2 always                           */
 #define B2K_OPT_COLLECT       9  /* saturated partial lists are re-scanned by K-collect: 1 on (default), 0 = exhaustive scan */
 #define B2K_OPT_SEED          7  /* K-score threshold seeding from a sampling pass: 1 auto (default), 0 off, N > 1 = N sample tiles per split */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs above 128 queries unless the last 256-query */

@@ -18,7 +18,7 @@ echo "score_tc2 capture exit $?"
 ncu --set full --clock-control none --import-source on -k regex:score_tc_kernel -s 11 -c 1 -o gpurun_out/prof_score_tc_b1 \
     $CMD > gpurun_out/ncu_tc_b1.log 2>&1
 echo "score_tc (batch 1) capture exit $?"
-ncu --set full --clock-control none --import-source on -k regex:pack_rows_kernel -s 170 -c 1 -o gpurun_out/prof_pack \
+ncu --set full --clock-control none --import-source on -k regex:pack_rows_kernel -s 156 -c 1 -o gpurun_out/prof_pack \
     $CMD > gpurun_out/ncu_pack.log 2>&1
 echo "pack capture exit $?"
 ls -la gpurun_out/*.ncu-rep

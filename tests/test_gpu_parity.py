@@ -167,7 +167,7 @@ def test_threshold_tightening_keeps_bits_and_cuts_candidates_tc(db20k):
     for path in ("scan", "tc2"):
         _set_path(ix, path)
         for on in (0, 1):
-            ix.set_option(_capi.OPT_TIGHTEN, 2 * on)          # 2 = always (1 = auto: only from 256 queries)
+            ix.set_option(_capi.OPT_TIGHTEN, 2 * on)          # 2 = always (1 = auto: only from 32 queries)
             st = _check(ix, pk, q[:4] if path == "scan" else q, 10)
             cands[(path, on)] = st["n_candidates"] / st["n_queries"]
             assert st["n_uncertified"] == 0
