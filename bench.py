@@ -459,6 +459,31 @@ def main():
     else:
         alt_ms = None
 
+    # ---- yardstick (never on the product path): the library GEMM on THIS contraction's shape, scores only
+    # (bf16 output written to HBM, no top-k), on the same box right after the fused kernel — the bf16 peak in
+    # MEASURED_PEAKS.json comes from an 8192^3 GEMM, which this K = 1984 shape cannot reach in any kernel
+    yard = None
+    if rank == 0 and B >= 1024:
+        try:
+            n_y = 262144
+            qy = torch.randn(B, Dp, device=dev, dtype=torch.bfloat16)
+            dby = torch.randn(n_y, Dp, device=dev, dtype=torch.bfloat16)
+            outy = torch.empty(B, n_y, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                torch.matmul(qy, dby.t(), out=outy)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                torch.matmul(qy, dby.t(), out=outy)
+            e1.record()
+            torch.cuda.synchronize()
+            yard = {"what": f"torch.matmul (cuBLAS) bf16 {B}x{n_y}x{Dp}, scores only, no top-k; yardstick, not the product path",
+                    "tflops": 2.0 * B * n_y * D / (e0.elapsed_time(e1) / 10) / 1e9}
+            del qy, dby, outy
+        except Exception as e:      # a yardstick must never fail the bench
+            yard = {"error": str(e)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_rows = max(1024, min(args.cpu_rows, int(args.cpu_rows * 1968 / D)))
@@ -491,6 +516,7 @@ def main():
                       "nccl_path_ms": alt_ms, "build_rows_per_s": n_local / build_s,
                       "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * Dp) / build_s / 1e9,
                       "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep,
+                      "library_gemm_same_shape": yard,
                       "hnsw_baseline": hnsw},
         }
         print(json.dumps(line), flush=True)
