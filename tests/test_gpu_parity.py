@@ -576,3 +576,37 @@ def test_config5_per_gpu_capacity_slice(gpu):
     d, l = ix.search(f, 1)
     assert l[0, 0] == 99_999_999 and d[0, 0] < 1e-5
     ix.close()
+
+
+def test_sharded_index_single_rank_and_row_ranges(gpu, tmp_path, db20k):
+    """ShardedIndex (the faiss-protocol object ImageRecommender uses under torchrun): with one rank it is
+    the whole file; two row-range loads of the same file merged by K-merge give the same bits — the
+    arithmetic of the N > 1 deployment without needing N GPUs (the real thing: scripts/check_sharded.py)."""
+    import torch
+    irb = _irb()
+    from image_recommender_b200.sharded import ShardedIndex, shard_range
+    ix, pk, n = db20k
+    p = tmp_path / "index_hnsw_color_sift_dreamsim.faiss"
+    ix.save(p, np.arange(n, dtype=np.int64))
+    q = oracle.synth_queries(DIMS, 37, n, n_clusters=8, qseed=321)
+    want = oracle.search_exact(pk["f32"], q, 10, pk["norm2"])
+    sh = ShardedIndex.load(p, device=gpu)
+    assert sh.ntotal == n and sh.d == sum(DIMS)
+    d, l = sh.search(q, 10)
+    assert np.array_equal(l, want[1]) and np.array_equal(d.view(np.uint32), want[0].view(np.uint32))
+    sh.close()
+    parts = []
+    qd = torch.from_numpy(q).cuda(gpu)
+    for r in range(3):
+        r0, r1 = shard_range(n, 3, r)
+        part = irb.FlatShard.load(p, device=gpu, row_begin=r0, row_end=r1)
+        assert part.base_offset == r0 and part.ntotal == r1 - r0
+        parts.append([t.clone() for t in part.search_device(qd, 10)])
+        part.close()
+    m_dist, m_lab, m_ip = irb.merge_topk_device(torch.stack([x[2] for x in parts]).contiguous(),
+                                                torch.stack([x[0] for x in parts]).contiguous(),
+                                                torch.stack([x[1] for x in parts]).contiguous())
+    torch.cuda.synchronize()
+    assert np.array_equal(m_lab.cpu().numpy(), want[1])
+    assert np.array_equal(m_dist.cpu().numpy().view(np.uint32), want[0].view(np.uint32))
+    assert np.array_equal(m_ip.cpu().numpy().view(np.uint32), want[2].view(np.uint32))
