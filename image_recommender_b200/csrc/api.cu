@@ -108,6 +108,7 @@ struct b2k_index {
   int opt_seed = 1;                           // threshold seeding for the tcgen05 paths
   int opt_tighten = 1;                        // exact-score tightening of the candidate threshold
   int opt_collect = 1;                        // K-collect serves saturated lists (else: exhaustive scan)
+  int opt_inline_seed = 1;                    // single-CTA kernel: seeding inside the main launch when eligible
   // options
   int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 0, opt_splits = 0;
   b2k_stats stats;
@@ -177,7 +178,7 @@ int ensure_workspace(b2k_index* ix, int nq, int k) {
   if ((rc = dev_alloc(&w.cand_ip, (size_t)cap * cand_cap))) return rc;
   if ((rc = dev_alloc(&w.cand_count, cap))) return rc;
   if ((rc = dev_alloc(&w.flags, cap))) return rc;
-  if ((rc = dev_alloc(&w.fail_count, 2))) return rc;      // [0] failed queries, [1] saturated pairs
+  if ((rc = dev_alloc(&w.fail_count, 4))) return rc;      // [0] failed queries, [1] saturated pairs, [2..3] grid barrier
   if ((rc = dev_alloc(&w.fail_list, cap))) return rc;
   if ((rc = dev_alloc(&w.exact_partial, (size_t)cap * exact_splits * kList))) return rc;
   if ((rc = dev_alloc(&w.exact_ceil, cap))) return rc;
@@ -204,12 +205,12 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
 
   QueryPrepArgs qp;
   qp.q = q_dev; qp.q_bf16 = path == 1 ? nullptr : w.q_bf16; qp.qn2 = w.qn2; qp.eps_scan = w.eps_scan;
-  qp.eps_tc = w.eps_tc; qp.stat_bits = ix->stat_bits;
+  qp.eps_tc = w.eps_tc; qp.stat_bits = ix->stat_bits; qp.floor_init = w.thr_floor;
   qp.nq = nq; qp.nq_pad = path == 1 ? nq : nq_pad; qp.D = ix->D; qp.Dp = ix->Dp;
   int rc = launch_query_prep(qp, st);
   if (rc) return rc;
   ++launches;
-  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, 2 * sizeof(int32_t), st));
+  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
 
   int n_lists_used = 0, split_tile_rows = 0;
   const float* eps = nullptr;
@@ -251,6 +252,8 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     ta.plan = pair ? score_tc2_plan(nq, ix->ntotal, ix->n_sm, forced, min_splits)
                    : score_tc_plan(nq, ix->ntotal, ix->n_sm, forced, min_splits);
     ta.partial = w.partial; ta.n_lists = w.n_lists; ta.max_tiles = 0; ta.thr_floor = nullptr;
+    ta.seed_k = 0; ta.seed_tile = 0; ta.seed_eps = w.eps_tc; ta.seed_floor = w.thr_floor;
+    ta.grid_bar = reinterpret_cast<unsigned int*>(w.fail_count + 2);
     // Threshold seeding: a sampling pass over the first tiles of every split bounds each query's
     // k-th best score from below, so the full pass admits only rows that can still matter and
     // the fused selection stops being the epilogue's bottleneck (DESIGN.md "seeding").
@@ -258,11 +261,19 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     const int64_t tiles_per_split = tiles_total / ta.plan.n_splits;
     // tiny batches on short splits: one launch without a floor beats sampling + seeding + main pass
     // (a single live query per warp inserts without divergence; gpurun_out/exp_path.log)
-    const bool seed = ix->opt_seed && tiles_per_split >= 16 && (ix->opt_seed > 1 || nq > 4 || tiles_per_split >= 128);
+    bool seed = ix->opt_seed && tiles_per_split >= 16 && (ix->opt_seed > 1 || nq > 4 || tiles_per_split >= 128);
     // sample ~0.75 % of the shard whatever the split count: a smaller sample leaves the floor too low
     // (more list insertions in the main pass), a larger one costs more than it saves
     int sample_tiles = ix->opt_seed > 1 ? ix->opt_seed : (int)((tiles_per_split * 3 + 200) / 400);
     sample_tiles = (int)std::max<int64_t>(1, std::min<int64_t>(sample_tiles, tiles_per_split / 8));
+    // One query tile on the single-CTA kernel = one resident CTA per split: the sampling pass, the seed
+    // kernel and the re-read of the sampled tiles fold into the main launch (in-kernel seeding).
+    if (seed && !pair && ix->opt_inline_seed && ix->opt_seed == 1 && k <= kList && ta.plan.n_qtiles == 1 &&
+        nq <= ta.plan.n_splits && ta.plan.n_splits <= ix->n_sm && ta.plan.n_splits <= 160) {
+      ta.seed_k = k;
+      ta.seed_tile = tiles_per_split >= 128 ? 1 : 0;
+      seed = false;
+    }
     if (seed) {
       ta.max_tiles = sample_tiles;
       rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
@@ -741,6 +752,8 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
       ix->opt_tighten = (int)value; return 0;
     case B2K_OPT_COLLECT:
       ix->opt_collect = value != 0; return 0;
+    case B2K_OPT_INLINE_SEED:
+      ix->opt_inline_seed = value != 0; return 0;
     case B2K_OPT_SEED:
       if (value < 0 || value > 4096) break;
       ix->opt_seed = (int)value; return 0;

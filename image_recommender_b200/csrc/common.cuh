@@ -105,6 +105,12 @@ __device__ __forceinline__ float lane_sumsq(const float* __restrict__ x, int d, 
   return p;
 }
 
+// score of an order-preserving key - 2*eps, rounded down (conservative candidate threshold)
+__device__ __forceinline__ float key_minus_2eps(uint32_t key, float eps) {
+  const uint32_t b = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  return __fsub_rd(__uint_as_float(b), __fmul_ru(2.0f, eps));
+}
+
 // Lane-partial of Spec R's exact score: fp32 products accumulated in fp64, element i owned by lane
 // (i/4) % 32 and folded in increasing i (combine the lanes with warp_sum_f64, round once to fp32).
 // The row is a latency-bound gather, so eight 16-byte loads per lane are issued before the dependent

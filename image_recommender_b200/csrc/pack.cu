@@ -164,6 +164,7 @@ query_prep_kernel(QueryPrepArgs a) {
   }
   const float qb2 = warp_sum_f32(pb), qd2 = warp_sum_f32(pd);
   if (lane == 0) {
+    if (a.floor_init) a.floor_init[w] = -INFINITY;
     a.qn2[w] = qn2;
     const float E = sqrtf(__uint_as_float(a.stat_bits[0])) * 1.001f;
     const float X = sqrtf(__uint_as_float(a.stat_bits[1])) * 1.001f;

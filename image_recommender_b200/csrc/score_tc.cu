@@ -28,10 +28,37 @@ constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageByt
 constexpr uint32_t kIdesc = make_idesc(kBlockM, kBlockN);
 }  // namespace
 
+namespace {
+constexpr int kSeedKeysPerThread = 40;        // 128 epilogue threads x 40 >= 160 lists x 32 entries
+
+__device__ __forceinline__ Cand load_cand_cg(const Cand* p) {
+  const long long v = __ldcg(reinterpret_cast<const long long*>(p));   // other CTAs wrote it: bypass L1
+  Cand c;
+  c.score = __int_as_float((int)(v & 0xffffffffll));
+  c.row = (int32_t)(v >> 32);
+  return c;
+}
+
+// Counter barrier across the (co-resident) CTAs of the grid: 1 = everyone arrived, 0 = gave up.
+__device__ __forceinline__ uint32_t grid_barrier_arrive_wait(unsigned int* ctr, unsigned int n) {
+  __threadfence();
+  atomicAdd(ctr, 1u);
+  for (unsigned int spins = 0; spins < (1u << 21); ++spins) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= n) return 1u;
+    __nanosleep(40);
+  }
+  return 0u;
+}
+}  // namespace
+
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                 int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
-                int32_t n_lists, int32_t max_tiles, const float* __restrict__ thr_floor, Cand* __restrict__ partial) {
+                int32_t n_lists, int32_t max_tiles, const float* __restrict__ thr_floor, Cand* __restrict__ partial,
+                int32_t seed_k, int32_t seed_tile, const float* __restrict__ seed_eps, float* seed_floor,
+                unsigned int* grid_bar) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -43,6 +70,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* tfull = empty + kStages;      // [2] accumulator ready
   uint64_t* tempty = tfull + 2;           // [2] accumulator drained
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* seed_scratch = tmem_base_slot + 4;      // [12] in-kernel seeding: cross-warp reductions, barrier verdicts
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtile = blockIdx.x % n_qtiles;
@@ -119,9 +147,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t r_addr = ptx::smem_u32(lrow + m);
     list_init(s_addr, r_addr);
     // padded query rows (qi >= nq) never insert; seeded floor = b_k(sample) - 2 eps (api.cu)
-    const float floor = qi < nq ? (thr_floor ? thr_floor[qi] : -INFINITY) : INFINITY;
+    float floor = qi < nq ? (thr_floor ? thr_floor[qi] : -INFINITY) : INFINITY;
     float thr = floor;
     int min_e = 0;
+    // no floor known for any live query of this warp: build the list of the first tile in bulk
+    const bool bulk_first = __all_sync(0xffffffffu, qi >= nq || floor == -INFINITY);
+    const int et = threadIdx.x - 64;                               // 0..127 among the epilogue threads
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
       const int64_t row0 = (tile_begin + t) * kBlockN;
@@ -129,10 +160,74 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
-      drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
+      if (t == 0 && bulk_first) drain_first_tile(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
+      else drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      if (seed_k > 0 && t == seed_tile && t + 1 < n_tiles) {
+        // ---- in-kernel seeding: what the sampling pass + seed_kernel do in two extra launches, without
+        // re-reading the sampled tiles.  Every CTA of the grid is resident (one per SM), so a counter
+        // barrier is safe; the spins are bounded and a CTA that gives up simply keeps its own floor.
+        // (A non-blocking variant — publish, keep draining, pick the floor up when it shows — measured
+        // slower: the tiles scored meanwhile insert against an unseeded threshold.)
+        if (qi < nq) list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
+        __threadfence();
+        ptx::named_bar_sync(2, 128);
+        if (et == 0) seed_scratch[8] = grid_barrier_arrive_wait(grid_bar + 0, (unsigned)n_splits);
+        ptx::named_bar_sync(2, 128);
+        const bool lists_ready = seed_scratch[8] != 0u;
+        if (lists_ready && split < nq) {
+          // this CTA owns query `split`: k-th best score over the n_splits exchanged lists
+          const Cand* ql = partial + (int64_t)split * n_lists * kList;
+          const int E = n_splits * kList;
+          uint32_t key[kSeedKeysPerThread];
+#pragma unroll
+          for (int u = 0; u < kSeedKeysPerThread; ++u) {
+            const int e = et + u * 128;
+            uint32_t kk = 0u;
+            if (e < E) {
+              const Cand c = load_cand_cg(ql + e);
+              kk = c.row < 0 ? 0u : float_key(c.score);
+            }
+            key[u] = kk;
+          }
+          uint32_t prev = 0xffffffffu, bk = 0u;
+          int seen = 0;
+          for (int pass = 0; pass < seed_k && seen < seed_k; ++pass) {
+            uint32_t m = 0u;
+#pragma unroll
+            for (int u = 0; u < kSeedKeysPerThread; ++u) if (key[u] < prev && key[u] > m) m = key[u];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) seed_scratch[quarter] = m;
+            ptx::named_bar_sync(2, 128);
+            m = max(max(seed_scratch[0], seed_scratch[1]), max(seed_scratch[2], seed_scratch[3]));
+            int c = 0;
+#pragma unroll
+            for (int u = 0; u < kSeedKeysPerThread; ++u) c += (key[u] == m && m != 0u) ? 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) seed_scratch[4 + quarter] = (uint32_t)c;
+            ptx::named_bar_sync(2, 128);
+            c = (int)(seed_scratch[4] + seed_scratch[5] + seed_scratch[6] + seed_scratch[7]);
+            ptx::named_bar_sync(2, 128);                          // scratch is rewritten by the next pass
+            if (m == 0u) break;                                   // fewer than k rows listed: no floor
+            seen += c;
+            prev = m;
+            if (seen >= seed_k) bk = m;
+          }
+          if (et == 0 && bk != 0u) seed_floor[split] = nextafterf(key_minus_2eps(bk, seed_eps[split]), -INFINITY);
+        }
+        __threadfence();
+        ptx::named_bar_sync(2, 128);
+        if (et == 0) seed_scratch[9] = lists_ready ? grid_barrier_arrive_wait(grid_bar + 1, (unsigned)n_splits) : 0u;
+        ptx::named_bar_sync(2, 128);
+        if (seed_scratch[9] != 0u && qi < nq) {
+          floor = fmaxf(floor, __ldcg(seed_floor + qi));
+          thr = fmaxf(thr, floor);
+        }
+      }
     }
     if (qi < nq) {
       list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
@@ -219,7 +314,7 @@ int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st) {
   const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(a.tmap_db);
   score_tc_kernel<<<a.plan.grid, kThreads, kSmemBytes, st>>>(*mq, *md, a.n_rows, a.Dp / kBlockK, a.nq,
                                                             a.plan.n_qtiles, a.plan.n_splits, a.n_lists, a.max_tiles, a.thr_floor,
-                                                            a.partial);
+                                                            a.partial, a.seed_k, a.seed_tile, a.seed_eps, a.seed_floor, a.grid_bar);
   B2K_CHECK_LAUNCH();
   return 0;
 }

@@ -126,6 +126,8 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const float floor = qi < nq ? (thr_floor ? thr_floor[qi] : -INFINITY) : INFINITY;
     float thr = floor;
     int min_e = 0;
+    // no floor known for any live query of this warp: build the list of the first tile in bulk
+    const bool bulk_first = __all_sync(0xffffffffu, qi >= nq || floor == -INFINITY);
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
       const int64_t row0 = (tile_begin + t) * kBlockN;
@@ -133,7 +135,8 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
-      drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
+      if (t == 0 && bulk_first) drain_first_tile(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
+      else drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_remote(&tempty[acc], 0);          // the leader's barrier

@@ -101,12 +101,6 @@ __device__ __forceinline__ void load_list_keys(const Cand* lst, int E, uint64_t*
   __syncthreads();
 }
 
-// score of key - 2*eps, rounded down (conservative)
-__device__ __forceinline__ float key_minus_2eps(uint32_t key, float eps) {
-  const uint32_t b = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
-  return __fsub_rd(__uint_as_float(b), __fmul_ru(2.0f, eps));
-}
-
 }  // namespace
 
 // ---------------------------------------------------------------------------------------

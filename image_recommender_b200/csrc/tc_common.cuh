@@ -101,6 +101,83 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, int64_t row0, 
   }
 }
 
+// First accumulator of a CTA when no admission floor is known yet (unseeded launch, in-kernel seeding):
+// filling an empty top-32 list element by element costs ~100 insertions per query, serialised over the
+// lanes of the warp (60-100 us at 128 live queries, which stalls the stream).  Instead the 256 columns are
+// read twice from TMEM (the accumulator stays there until it is released): pass 1 writes the maximum of
+// each 8-column group straight into list entry (column / 8) — 32 distinct rows, no rescans — and one
+// rescan yields the threshold; pass 2 inserts only the columns above it that are not their group's maximum
+// (a dozen).  `live` = this thread owns a real query (padded rows keep thr = +inf and write nothing).
+// Warp-collective: every lane of the warp must call it (tcgen05.ld is .sync.aligned).
+__device__ __forceinline__ void drain_first_tile(uint32_t taddr, int64_t row0, int valid, uint32_t s_addr,
+                                                 uint32_t r_addr, bool live, float floor, float& thr, int& min_e) {
+  uint64_t code_lo = 0ull;       // 3-bit arg-max of group (c, g) at bit 12*c + 3*g, chunks 0..3
+  uint64_t code_hi = 0ull;       // chunks 4..7
+#pragma unroll 1
+  for (int c = 0; c < kBlockN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+    ptx::tmem_ld_wait();
+    const int nvalid = valid - c * 32;
+    uint32_t code = 0u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float m = -INFINITY;
+      int a = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = (g * 8 + i) < nvalid ? __uint_as_float(v[g * 8 + i]) : -INFINITY;
+        if (x > m) { m = x; a = i; }
+      }
+      code |= (uint32_t)a << (3 * g);
+      if (live) {
+        const uint32_t e = (uint32_t)(c * 4 + g);
+        sts_f32(s_addr + e * kEntryStride, m);
+        sts_s32(r_addr + e * kEntryStride, m > -INFINITY ? (int32_t)(row0 + c * 32 + g * 8 + a) : -1);
+      }
+    }
+    if (c < 4) code_lo |= (uint64_t)code << (12 * c);
+    else code_hi |= (uint64_t)code << (12 * (c - 4));
+  }
+  if (live) {
+    float mn = INFINITY;
+    int me = 0;
+#pragma unroll
+    for (int e = 0; e < kList; ++e) {
+      const float se = lds_f32(s_addr + (uint32_t)e * kEntryStride);
+      if (se < mn) { mn = se; me = e; }
+    }
+    thr = fmaxf(mn, floor);
+    min_e = me;
+  }
+#pragma unroll 1
+  for (int c = 0; c < kBlockN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+    ptx::tmem_ld_wait();
+    const int nvalid = valid - c * 32;
+    const uint32_t code = (uint32_t)((c < 4 ? code_lo >> (12 * c) : code_hi >> (12 * (c - 4))) & 0xfffull);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const bool is_group_max = ((code >> (3 * (j >> 3))) & 7u) == (uint32_t)(j & 7);
+      if (j >= nvalid || is_group_max) v[j] = 0xff800000u;       // -inf: listed already, or not a row
+      mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    if (mx > thr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float sc = __uint_as_float(v[j]);
+        if (sc > thr) {
+          const uint64_t r = list_insert(s_addr, r_addr, min_e, sc, (int32_t)(row0 + c * 32 + j));
+          thr = fmaxf(__uint_as_float((uint32_t)r), floor);
+          min_e = (int)(r >> 32);
+        }
+      }
+    }
+  }
+}
+
 // Epilogue prologue / epilogue shared by both kernels.
 __device__ __forceinline__ void list_init(uint32_t s_addr, uint32_t r_addr) {
 #pragma unroll

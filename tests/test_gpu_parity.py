@@ -461,6 +461,26 @@ def test_large_scale_properties_tc(gpu):
         assert np.array_equal(res["scan"][0], res[other][0][:8])
         assert np.array_equal(res["scan"][1].view(np.uint32), res[other][1][:8].view(np.uint32))
     assert np.array_equal(res["tc"][0], res["tc2"][0])
+    # in-kernel seeding (single-CTA kernel, <= 128 queries: the CTAs exchange their lists after the first
+    # tile and continue with a global floor) against the three-launch seeding and no seeding at all
+    from image_recommender_b200 import _capi
+    _set_path(ix, "tc")
+    got = {}
+    for name, inline, seed, launches in (("inline", 1, 1, 8), ("three_launch", 0, 1, 10), ("unseeded", 0, 0, 8)):
+        ix.set_option(_capi.OPT_INLINE_SEED, inline)
+        ix.set_option(_capi.OPT_SEED, seed)
+        for m in (5, 64, 128):
+            dist, lab, ip = ix.search_device(q[:m].contiguous(), k)
+            torch.cuda.synchronize()
+            st = ix.stats()
+            assert st["launches"] == launches and st["n_uncertified"] == 0
+            got[(name, m)] = (lab.cpu().numpy(), ip.cpu().numpy(), st["n_candidates"])
+    for m in (5, 64, 128):
+        for name in ("three_launch", "unseeded"):
+            assert np.array_equal(got[("inline", m)][0], got[(name, m)][0])
+            assert np.array_equal(got[("inline", m)][1].view(np.uint32), got[(name, m)][1].view(np.uint32))
+        assert np.array_equal(got[("inline", m)][0], res["tc2"][0][:m])
+    ix.set_option(_capi.OPT_INLINE_SEED, 1); ix.set_option(_capi.OPT_SEED, 1)
     ix.close()
 
 
