@@ -326,7 +326,12 @@ def main():
         """Average device time of the scoring kernel (CUDA events inside the C ABI, on the
         launching stream) and of the tail kernels, over `steps` steady-state steps."""
         sc, tl, launches, unc = [], [], 0, 0
+        # stats() synchronises: small batches are preceded by two untimed back-to-back searches so that the
+        # timed kernel runs in the steady state of the timed region, not right after an idle gap
+        lead = 2 if qd.shape[0] <= 1024 else 0
         for _ in range(steps):
+            for _ in range(lead):
+                searcher.search_device(qd, k)
             searcher.search_device(qd, k)
             st = shard.stats()
             sc.append(st["score_ms"]); tl.append(st["tail_ms"]); launches = st["launches"]
@@ -472,14 +477,20 @@ def main():
             for _ in range(3):
                 torch.matmul(qy, dby.t(), out=outy)
             torch.cuda.synchronize()
+            # the fused kernel is timed inside steps of >= 100 ms (power-capped clocks): give the library the
+            # same regime — run for ~2 s, keep the last burst of 10 as the sustained figure, the first as burst
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(10):
-                torch.matmul(qy, dby.t(), out=outy)
-            e1.record()
-            torch.cuda.synchronize()
+            burst, sustained, t_start = None, None, time.perf_counter()
+            while sustained is None or time.perf_counter() - t_start < 2.0:
+                e0.record()
+                for _ in range(10):
+                    torch.matmul(qy, dby.t(), out=outy)
+                e1.record()
+                torch.cuda.synchronize()
+                sustained = 2.0 * B * n_y * D / (e0.elapsed_time(e1) / 10) / 1e9
+                burst = burst or sustained
             yard = {"what": f"torch.matmul (cuBLAS) bf16 {B}x{n_y}x{Dp}, scores only, no top-k; yardstick, not the product path",
-                    "tflops": 2.0 * B * n_y * D / (e0.elapsed_time(e1) / 10) / 1e9}
+                    "tflops_sustained": sustained, "tflops_burst": burst}
             del qy, dby, outy
         except Exception as e:      # a yardstick must never fail the bench
             yard = {"error": str(e)[:200]}
