@@ -423,13 +423,18 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description="Exact top-k image search on the GPU index")
     ap.add_argument("--db-path", default="images.db")
     ap.add_argument("--images-root", default="image_data")
-    ap.add_argument("--query", nargs="+", required=True, help="query image path(s); several are averaged")
+    ap.add_argument("--query", nargs="+", help="query image path(s); several are averaged")
+    ap.add_argument("--serve", action="store_true",
+                    help="resident mode: load the index once, then answer one query per stdin line (paths separated "
+                         "by spaces are averaged; results end with an empty line) until EOF")
     ap.add_argument("--index", default="color", help="e.g. combo_color_sift_dreamsim or color,sift")
     ap.add_argument("--top-k", type=int, default=5)
     ap.add_argument("--index-dir", default=".")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--plot", action="store_true")
     a = ap.parse_args(argv)
+    if not a.serve and not a.query:
+        ap.error("--query is required (or --serve)")
     import os
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if world > 1:       # torchrun --nproc-per-node G -m main.search_from_image ...: row-sharded over G GPUs
@@ -440,10 +445,31 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", a.device))
     rec = ImageRecommender(images_root=a.images_root, db_path=a.db_path, top_k=a.top_k, index_dir=a.index_dir,
                            device=a.device)
-    results = rec.search_similar_images(a.query, index_type=a.index, plot=a.plot and rank == 0)
-    if rank == 0:
-        for fp, dist_ in results or []:
-            print(f"{dist_:.6f}\t{fp}")
+    def answer(paths):
+        res = rec.search_similar_images(paths, index_type=a.index, plot=a.plot and rank == 0)
+        if rank == 0:
+            for fp, dist_ in res or []:
+                print(f"{dist_:.6f}\t{fp}")
+        return res
+
+    results = answer(a.query) if a.query else None
+    if a.serve:
+        # the index (and its id column) stays on the GPU between queries: SURVEY §8f-3.  Under torchrun every
+        # rank must see the same lines (give all ranks the same stdin, e.g. a file redirected into torchrun).
+        if rank == 0:
+            print(flush=True)
+        for line in sys.stdin:
+            paths = line.split()
+            if not paths:
+                continue
+            try:
+                results = answer(paths)
+            except Exception as e:          # a bad path must not take the server down
+                logging.error(f"query failed: {e}")
+                results = None
+            if rank == 0:
+                print(flush=True)
+        results = results or True
     rec.close()
     if world > 1:
         dist.destroy_process_group()

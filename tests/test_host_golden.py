@@ -3,6 +3,7 @@ golden vectors produced by the REAL reference code (tests/golden/make_golden.py)
 import pickle
 import shutil
 import sqlite3
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -224,6 +225,23 @@ def test_build_and_search_end_to_end(workdir, gpu):
     assert len(rec.search_similar_images(two, index_type="color,sift,dreamsim")) == 5
     groups = rec.search_batch([[two[0]], [two[1]], two], index_type="color,sift,dreamsim")
     assert [len(g) for g in groups] == [5, 5, 5] and groups[0][0][0] == rec.base_dir / paths[tab[0][0]]
+    # resident CLI mode: one process, index loaded once, one query per stdin line
+    import io
+    import contextlib
+    from main import search_from_image as sfi
+    out = io.StringIO()
+    stdin = sys.stdin
+    sys.stdin = io.StringIO(f"{two[0]}\n\n{two[0]} {two[1]}\nimage_data/set/missing.jpg\n{two[1]}\n")
+    try:
+        with contextlib.redirect_stdout(out):
+            rc = sfi.main(["--db-path", "images.db", "--images-root", "image_data", "--index", "combo_color_sift_dreamsim",
+                           "--top-k", "3", "--serve"])
+    finally:
+        sys.stdin = stdin
+    blocks = [b.strip().splitlines() for b in out.getvalue().split("\n\n")]
+    answers = [b for b in blocks if b and "\t" in b[0]]
+    assert rc == 0 and len(answers) == 3 and all(len(b) == 3 for b in answers)
+    assert answers[0][0].endswith(paths[tab[0][0]]) and answers[2][0].endswith(paths[tab[1][0]])
     # update_index appends only images without an offset
     conn = sqlite3.connect("images.db")
     v = lambda d: sqlite3.Binary(pickle.dumps((np.ones(d, np.float32) / np.sqrt(d)), protocol=pickle.HIGHEST_PROTOCOL))  # noqa: E731
