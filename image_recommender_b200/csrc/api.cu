@@ -252,7 +252,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     ta.plan = pair ? score_tc2_plan(nq, ix->ntotal, ix->n_sm, forced, min_splits)
                    : score_tc_plan(nq, ix->ntotal, ix->n_sm, forced, min_splits);
     ta.partial = w.partial; ta.n_lists = w.n_lists; ta.max_tiles = 0; ta.thr_floor = nullptr;
-    ta.seed_k = 0; ta.seed_tile = 0; ta.seed_eps = w.eps_tc; ta.seed_floor = w.thr_floor;
+    ta.seed_k = 0; ta.seed_eps = w.eps_tc; ta.seed_floor = w.thr_floor;
     ta.grid_bar = reinterpret_cast<unsigned int*>(w.fail_count + 2);
     // Threshold seeding: a sampling pass over the first tiles of every split bounds each query's
     // k-th best score from below, so the full pass admits only rows that can still matter and
@@ -271,7 +271,6 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     if (seed && !pair && ix->opt_inline_seed && ix->opt_seed == 1 && k <= kList && ta.plan.n_qtiles == 1 &&
         nq <= ta.plan.n_splits && ta.plan.n_splits <= ix->n_sm && ta.plan.n_splits <= 160) {
       ta.seed_k = k;
-      ta.seed_tile = tiles_per_split >= 128 ? 1 : 0;
       seed = false;
     }
     if (seed) {

@@ -185,11 +185,10 @@ struct ScoreTcArgs {
   int32_t n_lists;
   int32_t max_tiles;    // > 0: sampling pass, every split scores only its first max_tiles tiles
   const float* thr_floor;   // [nq] seeded admission floor (may be null)
-  // in-kernel seeding (single-CTA kernel, one query tile, every CTA resident): after `seed_tile + 1` tiles
-  // the CTAs exchange their lists through `partial`, CTA s computes query s's floor into seed_floor, and
-  // all continue with it.  seed_k = 0: off.  grid_bar: two zeroed counters.
+  // in-kernel seeding (single-CTA kernel, one query tile, every CTA resident): inside their first tile the
+  // CTAs exchange their lists through `partial`, CTA s computes query s's floor into seed_floor, and all
+  // continue with it.  seed_k = 0: off.  grid_bar: two zeroed counters.
   int32_t seed_k;
-  int32_t seed_tile;
   const float* seed_eps;    // [nq]
   float* seed_floor;        // [nq], pre-set to -inf
   unsigned int* grid_bar;   // [2]

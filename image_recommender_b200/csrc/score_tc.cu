@@ -24,9 +24,20 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kListBytes + 256;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kListBytes + 256 + 1024 /*seed_topk*/;
 constexpr uint32_t kIdesc = make_idesc(kBlockM, kBlockN);
 }  // namespace
+
+#ifdef B2K_PHASE_TIMERS
+__device__ unsigned long long g_tc_phase_t[2][8];
+#define B2K_TC_PHASE(i) do { if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && threadIdx.x == 64) { unsigned long long t_; \
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tc_phase_t[blockIdx.x == 0 ? 0 : 1][i] = t_; } } while (0)
+extern "C" int b2k_debug_tc_phase_times(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_tc_phase_t, sizeof(g_tc_phase_t));
+}
+#else
+#define B2K_TC_PHASE(i) do { } while (0)
+#endif
 
 namespace {
 constexpr int kSeedKeysPerThread = 40;        // 128 epilogue threads x 40 >= 160 lists x 32 entries
@@ -57,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                 int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
                 int32_t n_lists, int32_t max_tiles, const float* __restrict__ thr_floor, Cand* __restrict__ partial,
-                int32_t seed_k, int32_t seed_tile, const float* __restrict__ seed_eps, float* seed_floor,
+                int32_t seed_k, const float* __restrict__ seed_eps, float* seed_floor,
                 unsigned int* grid_bar) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -70,7 +81,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* tfull = empty + kStages;      // [2] accumulator ready
   uint64_t* tempty = tfull + 2;           // [2] accumulator drained
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint32_t* seed_scratch = tmem_base_slot + 4;      // [12] in-kernel seeding: cross-warp reductions, barrier verdicts
+  uint32_t* seed_scratch = tmem_base_slot + 4;      // [12] in-kernel seeding: barrier verdicts
+  uint64_t* seed_topk = reinterpret_cast<uint64_t*>(seed_scratch + 12);   // [4][32] per-warp top-k of the handler
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtile = blockIdx.x % n_qtiles;
@@ -153,6 +165,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // no floor known for any live query of this warp: build the list of the first tile in bulk
     const bool bulk_first = __all_sync(0xffffffffu, qi >= nq || floor == -INFINITY);
     const int et = threadIdx.x - 64;                               // 0..127 among the epilogue threads
+    B2K_TC_PHASE(0);
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
       const int64_t row0 = (tile_begin + t) * kBlockN;
@@ -160,78 +173,100 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
-      if (t == 0 && bulk_first) drain_first_tile(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
-      else drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
+      if (t == 0 && bulk_first) {
+        const FirstTileCodes codes = first_tile_pass1(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
+        if (seed_k > 0 && n_tiles > 1) {
+          // ---- in-kernel seeding: what the sampling pass + seed_kernel do in two extra launches, without
+          // re-reading the sampled tile.  The lists hold the 32 group maxima of the first tile; every CTA
+          // publishes them and arrives at a counter barrier (all CTAs of the grid are resident, one per SM;
+          // the spins are bounded and a CTA that gives up just keeps its own threshold); CTA s computes
+          // query s's k-th best over the exchanged lists and publishes the floor; the second pass over
+          // this tile and every later tile then admit only rows above it.  (A non-blocking variant —
+          // publish, keep draining, pick the floor up when it shows — measured slower: the tiles scored
+          // meanwhile insert against an unseeded threshold.)
+          B2K_TC_PHASE(1);
+          if (qi < nq) list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
+          __threadfence();
+          ptx::named_bar_sync(2, 128);
+          B2K_TC_PHASE(2);
+          if (et == 0) seed_scratch[8] = grid_barrier_arrive_wait(grid_bar + 0, (unsigned)n_splits);
+          ptx::named_bar_sync(2, 128);
+          B2K_TC_PHASE(3);
+          const bool lists_ready = seed_scratch[8] != 0u;
+          if (lists_ready && split < nq) {
+            // this CTA owns query `split`.  Any k distinct listed rows bound b_k from below, so the
+            // selection may drop rows as long as it never invents one: every lane keeps only the BEST of
+            // its ~37 entries (no passes over registers), the k best of the 128 lane maxima are then found
+            // with shuffles.  Two of the true top-k share a lane about once in three searches; the floor is
+            // then the (k+1)-th best instead of the k-th: still a lower bound, imperceptibly weaker.
+            const Cand* ql = partial + (int64_t)split * n_lists * kList;
+            const int E = n_splits * kList;
+            uint64_t best = 0ull;                                       // (score key << 32 | entry): unique
+            long long raw[kSeedKeysPerThread];                          // all loads in flight at once: the lists sit
+#pragma unroll                                                          // in other SMs' L2 slices, ~2 us away under load
+            for (int u = 0; u < kSeedKeysPerThread; ++u) {
+              const int e = (u * 4 + quarter) * 32 + lane;
+              raw[u] = e < E ? __ldcg(reinterpret_cast<const long long*>(ql + e)) : (long long)0xffffffff00000000ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kSeedKeysPerThread; ++u) {
+              const int e = (u * 4 + quarter) * 32 + lane;
+              const int32_t row = (int32_t)(raw[u] >> 32);
+              const uint32_t fk = row < 0 ? 0u : float_key(__int_as_float((int)(raw[u] & 0xffffffffll)));
+              const uint64_t kk = fk ? (((uint64_t)fk << 32) | (uint32_t)e) : 0ull;
+              best = kk > best ? kk : best;
+            }
+            uint64_t prev = ~0ull;
+            for (int j = 0; j < seed_k; ++j) {
+              uint64_t m = best < prev ? best : 0ull;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+              if (lane == 0) seed_topk[quarter * kList + j] = m;
+              prev = m;
+            }
+            ptx::named_bar_sync(2, 128);
+            if (quarter == 0) {
+              uint64_t c4[4];
+#pragma unroll
+              for (int w = 0; w < 4; ++w) c4[w] = lane < seed_k ? seed_topk[w * kList + lane] : 0ull;
+              uint64_t prev2 = ~0ull, bkey = 0ull;
+              for (int j = 0; j < seed_k; ++j) {
+                uint64_t m = 0ull;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) if (c4[w] < prev2 && c4[w] > m) m = c4[w];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+                prev2 = m;
+                bkey = m;
+              }
+              const uint32_t bk = (uint32_t)(bkey >> 32);               // 0: fewer than k rows listed, no floor
+              if (lane == 0 && bk != 0u) seed_floor[split] = nextafterf(key_minus_2eps(bk, seed_eps[split]), -INFINITY);
+            }
+          }
+          __threadfence();
+          ptx::named_bar_sync(2, 128);
+          B2K_TC_PHASE(4);
+          if (et == 0) seed_scratch[9] = lists_ready ? grid_barrier_arrive_wait(grid_bar + 1, (unsigned)n_splits) : 0u;
+          ptx::named_bar_sync(2, 128);
+          B2K_TC_PHASE(5);
+          if (seed_scratch[9] != 0u && qi < nq) {
+            floor = fmaxf(floor, __ldcg(seed_floor + qi));
+            thr = fmaxf(thr, floor);
+          }
+        }
+        first_tile_pass2(taddr, row0, valid, s_addr, r_addr, codes, floor, thr, min_e);
+      } else {
+        drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-      if (seed_k > 0 && t == seed_tile && t + 1 < n_tiles) {
-        // ---- in-kernel seeding: what the sampling pass + seed_kernel do in two extra launches, without
-        // re-reading the sampled tiles.  Every CTA of the grid is resident (one per SM), so a counter
-        // barrier is safe; the spins are bounded and a CTA that gives up simply keeps its own floor.
-        // (A non-blocking variant — publish, keep draining, pick the floor up when it shows — measured
-        // slower: the tiles scored meanwhile insert against an unseeded threshold.)
-        if (qi < nq) list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
-        __threadfence();
-        ptx::named_bar_sync(2, 128);
-        if (et == 0) seed_scratch[8] = grid_barrier_arrive_wait(grid_bar + 0, (unsigned)n_splits);
-        ptx::named_bar_sync(2, 128);
-        const bool lists_ready = seed_scratch[8] != 0u;
-        if (lists_ready && split < nq) {
-          // this CTA owns query `split`: k-th best score over the n_splits exchanged lists
-          const Cand* ql = partial + (int64_t)split * n_lists * kList;
-          const int E = n_splits * kList;
-          uint32_t key[kSeedKeysPerThread];
-#pragma unroll
-          for (int u = 0; u < kSeedKeysPerThread; ++u) {
-            const int e = et + u * 128;
-            uint32_t kk = 0u;
-            if (e < E) {
-              const Cand c = load_cand_cg(ql + e);
-              kk = c.row < 0 ? 0u : float_key(c.score);
-            }
-            key[u] = kk;
-          }
-          uint32_t prev = 0xffffffffu, bk = 0u;
-          int seen = 0;
-          for (int pass = 0; pass < seed_k && seen < seed_k; ++pass) {
-            uint32_t m = 0u;
-#pragma unroll
-            for (int u = 0; u < kSeedKeysPerThread; ++u) if (key[u] < prev && key[u] > m) m = key[u];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == 0) seed_scratch[quarter] = m;
-            ptx::named_bar_sync(2, 128);
-            m = max(max(seed_scratch[0], seed_scratch[1]), max(seed_scratch[2], seed_scratch[3]));
-            int c = 0;
-#pragma unroll
-            for (int u = 0; u < kSeedKeysPerThread; ++u) c += (key[u] == m && m != 0u) ? 1 : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) seed_scratch[4 + quarter] = (uint32_t)c;
-            ptx::named_bar_sync(2, 128);
-            c = (int)(seed_scratch[4] + seed_scratch[5] + seed_scratch[6] + seed_scratch[7]);
-            ptx::named_bar_sync(2, 128);                          // scratch is rewritten by the next pass
-            if (m == 0u) break;                                   // fewer than k rows listed: no floor
-            seen += c;
-            prev = m;
-            if (seen >= seed_k) bk = m;
-          }
-          if (et == 0 && bk != 0u) seed_floor[split] = nextafterf(key_minus_2eps(bk, seed_eps[split]), -INFINITY);
-        }
-        __threadfence();
-        ptx::named_bar_sync(2, 128);
-        if (et == 0) seed_scratch[9] = lists_ready ? grid_barrier_arrive_wait(grid_bar + 1, (unsigned)n_splits) : 0u;
-        ptx::named_bar_sync(2, 128);
-        if (seed_scratch[9] != 0u && qi < nq) {
-          floor = fmaxf(floor, __ldcg(seed_floor + qi));
-          thr = fmaxf(thr, floor);
-        }
-      }
     }
+    B2K_TC_PHASE(6);
     if (qi < nq) {
       list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
     }
+    B2K_TC_PHASE(7);
   }
 
   ptx::tc_fence_before();
@@ -314,7 +349,7 @@ int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st) {
   const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(a.tmap_db);
   score_tc_kernel<<<a.plan.grid, kThreads, kSmemBytes, st>>>(*mq, *md, a.n_rows, a.Dp / kBlockK, a.nq,
                                                             a.plan.n_qtiles, a.plan.n_splits, a.n_lists, a.max_tiles, a.thr_floor,
-                                                            a.partial, a.seed_k, a.seed_tile, a.seed_eps, a.seed_floor, a.grid_bar);
+                                                            a.partial, a.seed_k, a.seed_eps, a.seed_floor, a.grid_bar);
   B2K_CHECK_LAUNCH();
   return 0;
 }

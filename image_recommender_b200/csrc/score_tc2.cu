@@ -135,8 +135,12 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
-      if (t == 0 && bulk_first) drain_first_tile(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
-      else drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
+      if (t == 0 && bulk_first) {
+        const FirstTileCodes codes = first_tile_pass1(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
+        first_tile_pass2(taddr, row0, valid, s_addr, r_addr, codes, floor, thr, min_e);
+      } else {
+        drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_remote(&tempty[acc], 0);          // the leader's barrier

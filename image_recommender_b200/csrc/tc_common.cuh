@@ -104,15 +104,20 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, int64_t row0, 
 // First accumulator of a CTA when no admission floor is known yet (unseeded launch, in-kernel seeding):
 // filling an empty top-32 list element by element costs ~100 insertions per query, serialised over the
 // lanes of the warp (60-100 us at 128 live queries, which stalls the stream).  Instead the 256 columns are
-// read twice from TMEM (the accumulator stays there until it is released): pass 1 writes the maximum of
-// each 8-column group straight into list entry (column / 8) — 32 distinct rows, no rescans — and one
-// rescan yields the threshold; pass 2 inserts only the columns above it that are not their group's maximum
-// (a dozen).  `live` = this thread owns a real query (padded rows keep thr = +inf and write nothing).
-// Warp-collective: every lane of the warp must call it (tcgen05.ld is .sync.aligned).
-__device__ __forceinline__ void drain_first_tile(uint32_t taddr, int64_t row0, int valid, uint32_t s_addr,
-                                                 uint32_t r_addr, bool live, float floor, float& thr, int& min_e) {
-  uint64_t code_lo = 0ull;       // 3-bit arg-max of group (c, g) at bit 12*c + 3*g, chunks 0..3
-  uint64_t code_hi = 0ull;       // chunks 4..7
+// read twice from TMEM (the accumulator stays there until it is released):
+//   pass 1 writes the maximum of each 8-column group straight into list entry (column / 8) — 32 distinct
+//          rows, no rescans — and one rescan yields the threshold;
+//   pass 2 inserts only the columns above the threshold that are not their group's maximum (a dozen without
+//          a floor; next to none when the in-kernel seeding has published the floor between the passes).
+// `live` = this thread owns a real query (padded rows keep thr = +inf and write nothing).  Warp-collective:
+// every lane of the warp must call both (tcgen05.ld is .sync.aligned).
+struct FirstTileCodes {
+  uint64_t lo, hi;               // 3-bit arg-max of group (c, g) at bit 12*(c%4) + 3*g; lo: chunks 0..3, hi: 4..7
+};
+
+__device__ __forceinline__ FirstTileCodes first_tile_pass1(uint32_t taddr, int64_t row0, int valid, uint32_t s_addr,
+                                                          uint32_t r_addr, bool live, float floor, float& thr, int& min_e) {
+  FirstTileCodes codes{0ull, 0ull};
 #pragma unroll 1
   for (int c = 0; c < kBlockN / 32; ++c) {
     uint32_t v[32];
@@ -136,8 +141,8 @@ __device__ __forceinline__ void drain_first_tile(uint32_t taddr, int64_t row0, i
         sts_s32(r_addr + e * kEntryStride, m > -INFINITY ? (int32_t)(row0 + c * 32 + g * 8 + a) : -1);
       }
     }
-    if (c < 4) code_lo |= (uint64_t)code << (12 * c);
-    else code_hi |= (uint64_t)code << (12 * (c - 4));
+    if (c < 4) codes.lo |= (uint64_t)code << (12 * c);
+    else codes.hi |= (uint64_t)code << (12 * (c - 4));
   }
   if (live) {
     float mn = INFINITY;
@@ -150,13 +155,18 @@ __device__ __forceinline__ void drain_first_tile(uint32_t taddr, int64_t row0, i
     thr = fmaxf(mn, floor);
     min_e = me;
   }
+  return codes;
+}
+
+__device__ __forceinline__ void first_tile_pass2(uint32_t taddr, int64_t row0, int valid, uint32_t s_addr, uint32_t r_addr,
+                                                 FirstTileCodes codes, float floor, float& thr, int& min_e) {
 #pragma unroll 1
   for (int c = 0; c < kBlockN / 32; ++c) {
     uint32_t v[32];
     ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
     ptx::tmem_ld_wait();
     const int nvalid = valid - c * 32;
-    const uint32_t code = (uint32_t)((c < 4 ? code_lo >> (12 * c) : code_hi >> (12 * (c - 4))) & 0xfffull);
+    const uint32_t code = (uint32_t)((c < 4 ? codes.lo >> (12 * c) : codes.hi >> (12 * (c - 4))) & 0xfffull);
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -187,12 +197,16 @@ __device__ __forceinline__ void list_init(uint32_t s_addr, uint32_t r_addr) {
   }
 }
 __device__ __forceinline__ void list_store(uint32_t s_addr, uint32_t r_addr, Cand* out) {
-#pragma unroll 4
-  for (int e = 0; e < kList; ++e) {
-    Cand c;
-    c.score = lds_f32(s_addr + (uint32_t)e * kEntryStride);
-    c.row = lds_s32(r_addr + (uint32_t)e * kEntryStride);
-    out[e] = c;
+  // 32 (score, row) records = 256 contiguous, 256-byte aligned bytes per thread: sixteen 16-byte stores
+  uint4* o4 = reinterpret_cast<uint4*>(out);
+#pragma unroll 8
+  for (int e = 0; e < kList; e += 2) {
+    uint4 v;
+    v.x = __float_as_uint(lds_f32(s_addr + (uint32_t)e * kEntryStride));
+    v.y = (uint32_t)lds_s32(r_addr + (uint32_t)e * kEntryStride);
+    v.z = __float_as_uint(lds_f32(s_addr + (uint32_t)(e + 1) * kEntryStride));
+    v.w = (uint32_t)lds_s32(r_addr + (uint32_t)(e + 1) * kEntryStride);
+    o4[e >> 1] = v;
   }
 }
 
