@@ -50,7 +50,8 @@ typedef struct b2k_index b2k_index;
                                  /* batches of 32 queries and more), 0 off, 2 always                           */
 #define B2K_OPT_COLLECT       9  /* saturated partial lists are re-scanned by K-collect: 1 on (default), 0 = exhaustive scan */
 #define B2K_OPT_INLINE_SEED  10  /* <= 128 queries: seeding folded into the scoring launch (grid barrier): 1 on (default) */
-#define B2K_OPT_SEED          7  /* K-score threshold seeding from a sampling pass: 1 auto (default), 0 off, N > 1 = N sample tiles per split */
+#define B2K_OPT_SEED          7  /* K-score threshold seeding: 1 auto (default), 0 off, N > 1 = a sampling pass of  */
+                                 /* N tiles per split (forces the three-launch form, no in-kernel seeding)        */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs above 128 queries unless the last 256-query */
                                  /* tile would be half empty, up to 896 queries), 0 single CTA, 1 pairs          */
 
