@@ -630,3 +630,28 @@ def test_sharded_index_single_rank_and_row_ranges(gpu, tmp_path, db20k):
     assert np.array_equal(m_lab.cpu().numpy(), want[1])
     assert np.array_equal(m_dist.cpu().numpy().view(np.uint32), want[0].view(np.uint32))
     assert np.array_equal(m_ip.cpu().numpy().view(np.uint32), want[2].view(np.uint32))
+
+
+def test_more_queries_than_one_pass(gpu):
+    """nq beyond the per-pass workspace limit (16384): the host and device entry points split the batch;
+    results equal those of separate calls (and the oracle on a sample)."""
+    import torch
+    irb = _irb()
+    n, k = 900, 7
+    tabs, pk = _mk(n)
+    ix = irb.FlatShard(DIMS, n, device=gpu)
+    ix.add_tables(tabs)
+    nq = 16384 + 300
+    q = oracle.synth_queries(DIMS, nq, n, n_clusters=8, qseed=9)
+    dist, lab, ip = ix.search_ip(q, k)
+    d1, l1, i1 = ix.search_ip(q[:16384], k)
+    d2, l2, i2 = ix.search_ip(q[16384:], k)
+    assert np.array_equal(lab, np.concatenate([l1, l2])) and np.array_equal(dist.view(np.uint32), np.concatenate([d1, d2]).view(np.uint32))
+    sample = np.r_[0:50, 16380:16390, nq - 40:nq]
+    w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q[sample], k, pk["norm2"])
+    assert np.array_equal(lab[sample], w_lab) and np.array_equal(ip[sample].view(np.uint32), w_ip.view(np.uint32))
+    qd = torch.from_numpy(q).cuda(gpu)
+    dd, ld, _ = ix.search_device(qd, k)
+    torch.cuda.synchronize()
+    assert np.array_equal(ld.cpu().numpy(), lab) and np.array_equal(dd.cpu().numpy().view(np.uint32), dist.view(np.uint32))
+    ix.close()
