@@ -268,8 +268,10 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     sample_tiles = (int)std::max<int64_t>(1, std::min<int64_t>(sample_tiles, tiles_per_split / 8));
     // One query tile on the single-CTA kernel = one resident CTA per split: the sampling pass, the seed
     // kernel and the re-read of the sampled tiles fold into the main launch (in-kernel seeding).
-    if (seed && !pair && ix->opt_inline_seed && ix->opt_seed == 1 && k <= kList && ta.plan.n_qtiles == 1 &&
-        nq <= ta.plan.n_splits && ta.plan.n_splits <= ix->n_sm && ta.plan.n_splits <= 160) {
+    // (CTA pairs: up to 256 queries when the pairs of one query tile fill at most one wave.)
+    const int n_ctas = pair ? 2 * ta.plan.n_splits : ta.plan.n_splits;
+    if (seed && ix->opt_inline_seed && ix->opt_seed == 1 && k <= kList && ta.plan.n_qtiles == 1 &&
+        n_ctas <= ix->n_sm && ta.plan.n_splits <= 160 && nq <= (pair ? 2 : 1) * n_ctas) {
       ta.seed_k = k;
       seed = false;
     }

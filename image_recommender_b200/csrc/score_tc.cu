@@ -39,31 +39,6 @@ extern "C" int b2k_debug_tc_phase_times(unsigned long long* out) {
 #define B2K_TC_PHASE(i) do { } while (0)
 #endif
 
-namespace {
-constexpr int kSeedKeysPerThread = 40;        // 128 epilogue threads x 40 >= 160 lists x 32 entries
-
-__device__ __forceinline__ Cand load_cand_cg(const Cand* p) {
-  const long long v = __ldcg(reinterpret_cast<const long long*>(p));   // other CTAs wrote it: bypass L1
-  Cand c;
-  c.score = __int_as_float((int)(v & 0xffffffffll));
-  c.row = (int32_t)(v >> 32);
-  return c;
-}
-
-// Counter barrier across the (co-resident) CTAs of the grid: 1 = everyone arrived, 0 = gave up.
-__device__ __forceinline__ uint32_t grid_barrier_arrive_wait(unsigned int* ctr, unsigned int n) {
-  __threadfence();
-  atomicAdd(ctr, 1u);
-  for (unsigned int spins = 0; spins < (1u << 21); ++spins) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    if (v >= n) return 1u;
-    __nanosleep(40);
-  }
-  return 0u;
-}
-}  // namespace
-
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                 int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
@@ -176,83 +151,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (t == 0 && bulk_first) {
         const FirstTileCodes codes = first_tile_pass1(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
         if (seed_k > 0 && n_tiles > 1) {
-          // ---- in-kernel seeding: what the sampling pass + seed_kernel do in two extra launches, without
-          // re-reading the sampled tile.  The lists hold the 32 group maxima of the first tile; every CTA
-          // publishes them and arrives at a counter barrier (all CTAs of the grid are resident, one per SM;
-          // the spins are bounded and a CTA that gives up just keeps its own threshold); CTA s computes
-          // query s's k-th best over the exchanged lists and publishes the floor; the second pass over
-          // this tile and every later tile then admit only rows above it.  (A non-blocking variant —
-          // publish, keep draining, pick the floor up when it shows — measured slower: the tiles scored
-          // meanwhile insert against an unseeded threshold.)
           B2K_TC_PHASE(1);
-          if (qi < nq) list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
-          __threadfence();
-          ptx::named_bar_sync(2, 128);
-          B2K_TC_PHASE(2);
-          if (et == 0) seed_scratch[8] = grid_barrier_arrive_wait(grid_bar + 0, (unsigned)n_splits);
-          ptx::named_bar_sync(2, 128);
-          B2K_TC_PHASE(3);
-          const bool lists_ready = seed_scratch[8] != 0u;
-          if (lists_ready && split < nq) {
-            // this CTA owns query `split`.  Any k distinct listed rows bound b_k from below, so the
-            // selection may drop rows as long as it never invents one: every lane keeps only the BEST of
-            // its ~37 entries (no passes over registers), the k best of the 128 lane maxima are then found
-            // with shuffles.  Two of the true top-k share a lane about once in three searches; the floor is
-            // then the (k+1)-th best instead of the k-th: still a lower bound, imperceptibly weaker.
-            const Cand* ql = partial + (int64_t)split * n_lists * kList;
-            const int E = n_splits * kList;
-            uint64_t best = 0ull;                                       // (score key << 32 | entry): unique
-            long long raw[kSeedKeysPerThread];                          // all loads in flight at once: the lists sit
-#pragma unroll                                                          // in other SMs' L2 slices, ~2 us away under load
-            for (int u = 0; u < kSeedKeysPerThread; ++u) {
-              const int e = (u * 4 + quarter) * 32 + lane;
-              raw[u] = e < E ? __ldcg(reinterpret_cast<const long long*>(ql + e)) : (long long)0xffffffff00000000ull;
-            }
-#pragma unroll
-            for (int u = 0; u < kSeedKeysPerThread; ++u) {
-              const int e = (u * 4 + quarter) * 32 + lane;
-              const int32_t row = (int32_t)(raw[u] >> 32);
-              const uint32_t fk = row < 0 ? 0u : float_key(__int_as_float((int)(raw[u] & 0xffffffffll)));
-              const uint64_t kk = fk ? (((uint64_t)fk << 32) | (uint32_t)e) : 0ull;
-              best = kk > best ? kk : best;
-            }
-            uint64_t prev = ~0ull;
-            for (int j = 0; j < seed_k; ++j) {
-              uint64_t m = best < prev ? best : 0ull;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
-              if (lane == 0) seed_topk[quarter * kList + j] = m;
-              prev = m;
-            }
-            ptx::named_bar_sync(2, 128);
-            if (quarter == 0) {
-              uint64_t c4[4];
-#pragma unroll
-              for (int w = 0; w < 4; ++w) c4[w] = lane < seed_k ? seed_topk[w * kList + lane] : 0ull;
-              uint64_t prev2 = ~0ull, bkey = 0ull;
-              for (int j = 0; j < seed_k; ++j) {
-                uint64_t m = 0ull;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) if (c4[w] < prev2 && c4[w] > m) m = c4[w];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
-                prev2 = m;
-                bkey = m;
-              }
-              const uint32_t bk = (uint32_t)(bkey >> 32);               // 0: fewer than k rows listed, no floor
-              if (lane == 0 && bk != 0u) seed_floor[split] = nextafterf(key_minus_2eps(bk, seed_eps[split]), -INFINITY);
-            }
-          }
-          __threadfence();
-          ptx::named_bar_sync(2, 128);
-          B2K_TC_PHASE(4);
-          if (et == 0) seed_scratch[9] = lists_ready ? grid_barrier_arrive_wait(grid_bar + 1, (unsigned)n_splits) : 0u;
-          ptx::named_bar_sync(2, 128);
+          seed_exchange(seed_k, seed_eps, seed_floor, grid_bar, partial, n_lists, n_splits, nq, qi, split, s_addr, r_addr,
+                        /*cta_id=*/split, /*n_ctas=*/n_splits, seed_scratch, seed_topk, et, quarter, lane, floor, thr);
           B2K_TC_PHASE(5);
-          if (seed_scratch[9] != 0u && qi < nq) {
-            floor = fmaxf(floor, __ldcg(seed_floor + qi));
-            thr = fmaxf(thr, floor);
-          }
         }
         first_tile_pass2(taddr, row0, valid, s_addr, r_addr, codes, floor, thr, min_e);
       } else {

@@ -24,14 +24,15 @@ constexpr int kABytes2 = kBlockM * kBlockK * 2;          // 16 KB: this CTA's 12
 constexpr int kBHalfRows = kBlockN / 2;                  // 128 DB rows staged per CTA
 constexpr int kBBytes2 = kBHalfRows * kBlockK * 2;       // 16 KB
 constexpr int kStageBytes2 = kABytes2 + kBBytes2;        // 32 KB per CTA
-constexpr size_t kSmemBytes2 = 1024 + (size_t)kStages2 * kStageBytes2 + kListBytes + 256;
+constexpr size_t kSmemBytes2 = 1024 + (size_t)kStages2 * kStageBytes2 + kListBytes + 256 + 1024 /*seed_topk*/;
 constexpr uint32_t kIdesc2 = make_idesc(2 * kBlockM, kBlockN);   // M=256 across the pair
 }  // namespace
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
-                 int32_t n_lists, int32_t max_tiles, const float* __restrict__ thr_floor, Cand* __restrict__ partial) {
+                 int32_t n_lists, int32_t max_tiles, const float* __restrict__ thr_floor, Cand* __restrict__ partial,
+                 int32_t seed_k, const float* __restrict__ seed_eps, float* seed_floor, unsigned int* grid_bar) {
   extern __shared__ unsigned char smem_raw[];
   // identical carve-up in both CTAs: the MMA and the multicast commits address the peer by offset
   unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -44,6 +45,8 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* tfull = empty + kStages2;     // [2]
   uint64_t* tempty = tfull + 2;           // [2] used in the leader only
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* seed_scratch = tmem_base_slot + 4;      // [12] in-kernel seeding: barrier verdicts
+  uint64_t* seed_topk = reinterpret_cast<uint64_t*>(seed_scratch + 12);   // [4][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();          // 0 = leader
@@ -123,7 +126,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t r_addr = ptx::smem_u32(lrow + m);
     list_init(s_addr, r_addr);
     // padded query rows (qi >= nq) never insert; seeded floor = b_k(sample) - 2 eps (api.cu)
-    const float floor = qi < nq ? (thr_floor ? thr_floor[qi] : -INFINITY) : INFINITY;
+    float floor = qi < nq ? (thr_floor ? thr_floor[qi] : -INFINITY) : INFINITY;
     float thr = floor;
     int min_e = 0;
     // no floor known for any live query of this warp: build the list of the first tile in bulk
@@ -137,6 +140,12 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN);
       if (t == 0 && bulk_first) {
         const FirstTileCodes codes = first_tile_pass1(taddr, row0, valid, s_addr, r_addr, qi < nq, floor, thr, min_e);
+        // in-kernel seeding (tc_common.cuh) when every CTA of the grid is resident: one query tile, at most
+        // n_sm / 2 pairs; CTA c computes the floors of queries c and c + gridDim.x
+        if (seed_k > 0 && n_tiles > 1)
+          seed_exchange(seed_k, seed_eps, seed_floor, grid_bar, partial, n_lists, n_splits, nq, qi, split, s_addr, r_addr,
+                        /*cta_id=*/(int)blockIdx.x, /*n_ctas=*/(int)gridDim.x, seed_scratch, seed_topk,
+                        (int)threadIdx.x - 64, quarter, lane, floor, thr);
         first_tile_pass2(taddr, row0, valid, s_addr, r_addr, codes, floor, thr, min_e);
       } else {
         drain_accumulator(taddr, row0, valid, s_addr, r_addr, floor, thr, min_e);
@@ -196,7 +205,7 @@ int launch_score_tc2(const ScoreTcArgs& a, cudaStream_t st) {
   const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(a.tmap_db);
   score_tc2_kernel<<<a.plan.grid, kThreads, kSmemBytes2, st>>>(*mq, *md, a.n_rows, a.Dp / kBlockK, a.nq,
                                                               a.plan.n_qtiles, a.plan.n_splits, a.n_lists, a.max_tiles, a.thr_floor,
-                                                              a.partial);
+                                                              a.partial, a.seed_k, a.seed_eps, a.seed_floor, a.grid_bar);
   B2K_CHECK_LAUNCH();
   return 0;
 }

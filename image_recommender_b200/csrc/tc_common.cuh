@@ -210,6 +210,105 @@ __device__ __forceinline__ void list_store(uint32_t s_addr, uint32_t r_addr, Can
   }
 }
 
+// ---- in-kernel threshold seeding ---------------------------------------------------------------------------
+// What the sampling pass + seed_kernel do in two extra launches, without re-reading the sampled tile, for
+// grids whose CTAs are all resident at once (one CTA per SM).  Called by the 128 epilogue threads of a CTA
+// between the two passes over its first tile: the lists hold the 32 group maxima of that tile; every CTA
+// publishes them and arrives at a counter barrier (the spins are bounded and a CTA that gives up just keeps
+// its own threshold); CTA c computes the floors of queries c, c + n_ctas, ... from the exchanged lists and
+// publishes them; a second barrier, and the second pass over this tile and every later tile admit only rows
+// above the floor.  (A non-blocking variant — publish, keep draining, pick the floor up when it shows —
+// measured slower: the tiles scored meanwhile insert against an unseeded threshold.)
+constexpr int kSeedKeysPerThread = 40;        // 128 epilogue threads x 40 >= 160 lists x 32 entries
+
+// Counter barrier across the (co-resident) CTAs of the grid: 1 = everyone arrived, 0 = gave up.
+__device__ __forceinline__ uint32_t grid_barrier_arrive_wait(unsigned int* ctr, unsigned int n) {
+  __threadfence();
+  atomicAdd(ctr, 1u);
+  for (unsigned int spins = 0; spins < (1u << 21); ++spins) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= n) return 1u;
+    __nanosleep(40);
+  }
+  return 0u;
+}
+
+// scratch: 12 u32; topk: 4 x 32 u64 of shared memory private to the epilogue warps (named barrier 2).
+__device__ __forceinline__ void seed_exchange(int seed_k, const float* __restrict__ seed_eps, float* seed_floor,
+                                              unsigned int* grid_bar, Cand* partial, int n_lists, int n_splits, int nq,
+                                              int qi, int split, uint32_t s_addr, uint32_t r_addr, int cta_id, int n_ctas,
+                                              uint32_t* scratch, uint64_t* topk, int et, int quarter, int lane,
+                                              float& floor, float& thr) {
+  if (qi < nq) list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
+  __threadfence();
+  ptx::named_bar_sync(2, 128);
+  if (et == 0) scratch[8] = grid_barrier_arrive_wait(grid_bar + 0, (unsigned)n_ctas);
+  ptx::named_bar_sync(2, 128);
+  const bool lists_ready = scratch[8] != 0u;
+  if (lists_ready) {
+    for (int hq = cta_id; hq < nq; hq += n_ctas) {
+      // Any k distinct listed rows bound b_k from below, so the selection may drop rows as long as it never
+      // invents one: every lane keeps only the BEST of its ~37 entries (no passes over registers), the k
+      // best of the 128 lane maxima are then found with shuffles.  Two of the true top-k share a lane about
+      // once in three searches; the floor is then the (k+1)-th best instead of the k-th: still a lower
+      // bound, imperceptibly weaker.
+      const Cand* ql = partial + (int64_t)hq * n_lists * kList;
+      const int E = n_splits * kList;
+      uint64_t best = 0ull;                                       // (score key << 32 | entry): unique
+      long long raw[kSeedKeysPerThread];                          // all loads in flight at once: the lists sit in
+#pragma unroll                                                    // other SMs' L2 slices, ~2 us away under load
+      for (int u = 0; u < kSeedKeysPerThread; ++u) {
+        const int e = (u * 4 + quarter) * 32 + lane;
+        raw[u] = e < E ? __ldcg(reinterpret_cast<const long long*>(ql + e)) : (long long)0xffffffff00000000ull;
+      }
+#pragma unroll
+      for (int u = 0; u < kSeedKeysPerThread; ++u) {
+        const int e = (u * 4 + quarter) * 32 + lane;
+        const int32_t row = (int32_t)(raw[u] >> 32);
+        const uint32_t fk = row < 0 ? 0u : float_key(__int_as_float((int)(raw[u] & 0xffffffffll)));
+        const uint64_t kk = fk ? (((uint64_t)fk << 32) | (uint32_t)e) : 0ull;
+        best = kk > best ? kk : best;
+      }
+      uint64_t prev = ~0ull;
+      for (int j = 0; j < seed_k; ++j) {
+        uint64_t m = best < prev ? best : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+        if (lane == 0) topk[quarter * kList + j] = m;
+        prev = m;
+      }
+      ptx::named_bar_sync(2, 128);
+      if (quarter == 0) {
+        uint64_t c4[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) c4[w] = lane < seed_k ? topk[w * kList + lane] : 0ull;
+        uint64_t prev2 = ~0ull, bkey = 0ull;
+        for (int j = 0; j < seed_k; ++j) {
+          uint64_t m = 0ull;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) if (c4[w] < prev2 && c4[w] > m) m = c4[w];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+          prev2 = m;
+          bkey = m;
+        }
+        const uint32_t bk = (uint32_t)(bkey >> 32);               // 0: fewer than k rows listed, no floor
+        if (lane == 0 && bk != 0u) seed_floor[hq] = nextafterf(key_minus_2eps(bk, seed_eps[hq]), -INFINITY);
+      }
+      ptx::named_bar_sync(2, 128);                                // topk[] is rewritten for the next query
+    }
+  }
+  __threadfence();
+  ptx::named_bar_sync(2, 128);
+  if (et == 0) scratch[9] = lists_ready ? grid_barrier_arrive_wait(grid_bar + 1, (unsigned)n_ctas) : 0u;
+  ptx::named_bar_sync(2, 128);
+  if (scratch[9] != 0u && qi < nq) {
+    floor = fmaxf(floor, __ldcg(seed_floor + qi));
+    thr = fmaxf(thr, floor);
+  }
+}
+
 int encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 }}  // namespace b2k::tc

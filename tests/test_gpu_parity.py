@@ -146,6 +146,7 @@ def test_seeded_threshold_matches_oracle_tc(db20k, path):
     ix, pk, n = db20k
     _set_path(ix, path)
     ix.set_option(_capi.OPT_SPLITS, 4)
+    ix.set_option(_capi.OPT_INLINE_SEED, 0)            # the three-launch form (sampling pass, seed kernel, main pass)
     for nq, k in ((5, 10), (300, 10), (64, 32)):
         q = oracle.synth_queries(DIMS, nq, n, n_clusters=8, qseed=1000 + nq)
         for seed in (1, 0):
@@ -153,6 +154,14 @@ def test_seeded_threshold_matches_oracle_tc(db20k, path):
             st = _check(ix, pk, q, k)
             assert st["launches"] == (10 if seed else 8)
     ix.set_option(_capi.OPT_SEED, 1)
+    ix.set_option(_capi.OPT_INLINE_SEED, 1)
+    # in-kernel seeding where the grid is one wave (4 splits: 4 CTAs / 8 CTAs of 4 pairs): one scoring launch
+    for nq in ((3, 4) if path == "tc" else (5, 16)):
+        ix.set_option(_capi.OPT_SEED, 2)               # explicit sample size: three launches
+        q = oracle.synth_queries(DIMS, nq, n, n_clusters=8, qseed=2000 + nq)
+        assert _check(ix, pk, q, 10)["launches"] == 10
+        ix.set_option(_capi.OPT_SEED, 1)
+        assert _check(ix, pk, q, 10)["launches"] == 8      # tc2: in-kernel seeding; tc: <= 4 queries run unseeded
     ix.set_option(_capi.OPT_SPLITS, 0)
     _set_path(ix, "auto")
 
@@ -481,6 +490,20 @@ def test_large_scale_properties_tc(gpu):
             assert np.array_equal(got[("inline", m)][1].view(np.uint32), got[(name, m)][1].view(np.uint32))
         assert np.array_equal(got[("inline", m)][0], res["tc2"][0][:m])
     ix.set_option(_capi.OPT_INLINE_SEED, 1); ix.set_option(_capi.OPT_SEED, 1)
+    # the CTA-pair kernel does the same for one query tile (<= 256 queries) when its pairs fill one wave
+    _set_path(ix, "tc2")
+    for m in (130, 256):
+        outs = []
+        for inline, launches in ((1, 8), (0, 10)):
+            ix.set_option(_capi.OPT_INLINE_SEED, inline)
+            dist, lab, ip = ix.search_device(q[:m].contiguous(), k)
+            torch.cuda.synchronize()
+            st = ix.stats()
+            assert st["launches"] == launches and st["path"] == 3 and st["n_uncertified"] == 0
+            outs.append((lab.cpu().numpy(), ip.cpu().numpy()))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+        assert np.array_equal(outs[0][0], res["tc2"][0][:m])
+    ix.set_option(_capi.OPT_INLINE_SEED, 1)
     ix.close()
 
 
