@@ -83,6 +83,7 @@ SIGNATURES = {
     "b2k_xchg_merge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2k_normalize_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "b2k_save": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "b2k_save_shard": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "b2k_load": (C.c_int, [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
     "b2k_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -804,23 +804,14 @@ int b2k_normalize_l2(float* x_host, int64_t n, int32_t d, int32_t device) {
 }
 
 // ---- persistence -------------------------------------------------------------------------
-int b2k_save(b2k_index* ix, const char* path, const int64_t* ids, int64_t n_ids) {
-  if (!ix || !path) { set_error("save: bad argument"); return B2K_E_INVALID; }
-  if (ids && n_ids != ix->ntotal) { set_error("save: %lld ids for %lld rows", (long long)n_ids, (long long)ix->ntotal); return B2K_E_INVALID; }
-  DeviceGuard g(ix->device);
-  B2K_CUDA(cudaStreamSynchronize(ix->stream));
-  FILE* f = fopen(path, "wb");
-  if (!f) { set_error("save: cannot open %s", path); return B2K_E_IO; }
-  FileHeader h;
-  memset(&h, 0, sizeof(h));
-  memcpy(h.magic, "B2KIDX01", 8);
-  h.version = 1; h.n_tables = ix->n_tables;
-  for (int t = 0; t < ix->n_tables; ++t) h.dims[t] = ix->dims[t];
-  h.D = ix->D; h.has_ids = ids ? 1 : 0; h.n_rows = ix->ntotal;
-  h.rows_offset = sizeof(FileHeader);
-  h.ids_offset = h.rows_offset + ix->ntotal * (int64_t)ix->D * 4;
-  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
-  // device -> pinned slot (async D2H) -> fwrite; the copy of chunk i+1 overlaps the write of chunk i
+namespace {
+// Rows [0, ntotal) of the shard -> file rows [file_row_begin, ...) of a file laid out for file_total_rows rows.
+// device -> pinned slot (async D2H) -> fwrite; the copy of chunk i+1 overlaps the write of chunk i.
+int write_shard_rows(b2k_index* ix, FILE* f, const char* path, const int64_t* ids, int64_t file_row_begin,
+                     int64_t file_total_rows) {
+  const int64_t rows_offset = sizeof(FileHeader);
+  const int64_t ids_offset = rows_offset + file_total_rows * (int64_t)ix->D * 4;
+  bool ok = fseek(f, (long)(rows_offset + file_row_begin * (int64_t)ix->D * 4), SEEK_SET) == 0;
   const int64_t chunk = std::max<int64_t>(256, std::min<int64_t>(ix->stage_rows, ((int64_t)1 << 26) / ((int64_t)ix->D * 4)));
   float* pin[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -844,11 +835,73 @@ int b2k_save(b2k_index* ix, const char* path, const int64_t* ids, int64_t n_ids)
   }
   cudaStreamSynchronize(ix->stream);
   for (int s = 0; s < 2; ++s) { if (pin[s]) cudaFreeHost(pin[s]); if (ev[s]) cudaEventDestroy(ev[s]); }
-  if (e != cudaSuccess) { fclose(f); set_error("save: %s", cudaGetErrorString(e)); return (int)e; }
-  if (ok && ids && ix->ntotal > 0) ok = fwrite(ids, 8, (size_t)ix->ntotal, f) == (size_t)ix->ntotal;
-  ok = (fclose(f) == 0) && ok;
+  if (e != cudaSuccess) { set_error("save: %s", cudaGetErrorString(e)); return (int)e; }
+  if (ok && ids && ix->ntotal > 0)
+    ok = fseek(f, (long)(ids_offset + file_row_begin * 8), SEEK_SET) == 0 &&
+         fwrite(ids, 8, (size_t)ix->ntotal, f) == (size_t)ix->ntotal;
   if (!ok) { set_error("save: write to %s failed", path); return B2K_E_IO; }
   return 0;
+}
+
+void fill_header(const b2k_index* ix, FileHeader& h, int64_t total_rows, bool has_ids) {
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "B2KIDX01", 8);
+  h.version = 1; h.n_tables = ix->n_tables;
+  for (int t = 0; t < ix->n_tables; ++t) h.dims[t] = ix->dims[t];
+  h.D = ix->D; h.has_ids = has_ids ? 1 : 0; h.n_rows = total_rows;
+  h.rows_offset = sizeof(FileHeader);
+  h.ids_offset = h.rows_offset + total_rows * (int64_t)ix->D * 4;
+}
+}  // namespace
+
+int b2k_save(b2k_index* ix, const char* path, const int64_t* ids, int64_t n_ids) {
+  if (!ix || !path) { set_error("save: bad argument"); return B2K_E_INVALID; }
+  if (ids && n_ids != ix->ntotal) { set_error("save: %lld ids for %lld rows", (long long)n_ids, (long long)ix->ntotal); return B2K_E_INVALID; }
+  DeviceGuard g(ix->device);
+  B2K_CUDA(cudaStreamSynchronize(ix->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("save: cannot open %s", path); return B2K_E_IO; }
+  FileHeader h;
+  fill_header(ix, h, ix->ntotal, ids != nullptr);
+  int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? 0 : B2K_E_IO;
+  if (rc) set_error("save: write to %s failed", path);
+  if (!rc) rc = write_shard_rows(ix, f, path, ids, 0, ix->ntotal);
+  if (fclose(f) != 0 && !rc) { set_error("save: write to %s failed", path); rc = B2K_E_IO; }
+  return rc;
+}
+
+int b2k_save_shard(b2k_index* ix, const char* path, const int64_t* ids, int64_t file_row_begin, int64_t file_total_rows,
+                   int32_t create) {
+  if (!ix || !path || file_row_begin < 0 || file_row_begin + ix->ntotal > file_total_rows) {
+    set_error("save_shard: bad argument (rows [%lld, +%lld) of %lld)", (long long)file_row_begin,
+              ix ? (long long)ix->ntotal : 0ll, (long long)file_total_rows);
+    return B2K_E_INVALID;
+  }
+  DeviceGuard g(ix->device);
+  B2K_CUDA(cudaStreamSynchronize(ix->stream));
+  FILE* f = fopen(path, create ? "wb" : "r+b");
+  if (!f) { set_error("save_shard: cannot open %s", path); return B2K_E_IO; }
+  int rc = 0;
+  if (create) {
+    // the creating rank lays the whole file out (header + sparse extent); the others write into it afterwards
+    FileHeader h;
+    fill_header(ix, h, file_total_rows, ids != nullptr);
+    const int64_t size = h.ids_offset + (ids ? file_total_rows * 8 : 0);
+    if (fwrite(&h, sizeof(h), 1, f) != 1 || (size > (int64_t)sizeof(h) && (fseek(f, (long)(size - 1), SEEK_SET) != 0 || fputc(0, f) == EOF))) {
+      set_error("save_shard: cannot lay out %s", path);
+      rc = B2K_E_IO;
+    }
+  } else {
+    FileHeader h;
+    rc = read_header(f, h, path);
+    if (!rc && (h.n_rows != file_total_rows || h.D != ix->D || (h.has_ids != 0) != (ids != nullptr))) {
+      set_error("save_shard: %s was laid out for another index (%lld rows, D=%d)", path, (long long)h.n_rows, h.D);
+      rc = B2K_E_INVALID;
+    }
+  }
+  if (!rc) rc = write_shard_rows(ix, f, path, ids, file_row_begin, file_total_rows);
+  if (fclose(f) != 0 && !rc) { set_error("save_shard: write to %s failed", path); rc = B2K_E_IO; }
+  return rc;
 }
 
 int b2k_file_info(const char* path, int64_t* n_rows, int32_t* n_tables, int32_t* table_dims, int32_t* has_ids) {

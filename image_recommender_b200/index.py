@@ -213,6 +213,15 @@ class FlatShard:
         else:
             check(_lib.b2k_save(self._h, str(path).encode(), None, 0))
 
+    def save_shard(self, path: str, ids, file_row_begin: int, file_total_rows: int, create: bool) -> None:
+        """Row-sharded build: write this shard's rows (and ids) at their place in one shared index file."""
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            if ids.size != self.ntotal:
+                raise ValueError(f"save_shard: {ids.size} ids for {self.ntotal} rows")
+        check(_lib.b2k_save_shard(self._h, str(path).encode(), ids.ctypes.data if ids is not None else None,
+                                  int(file_row_begin), int(file_total_rows), 1 if create else 0))
+
     @classmethod
     def load(cls, path: str, device: int = 0, row_begin: int = 0, row_end: int = -1) -> "FlatShard":
         info = file_info(path)

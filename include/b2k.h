@@ -190,6 +190,12 @@ int b2k_normalize_l2(float* x_host, int64_t n, int32_t d, int32_t device);
  * load() reads rows [row_begin, row_end) of the file (row_end < 0: to the end) so that
  * each GPU of a row-sharded deployment loads only its shard. */
 int b2k_save(b2k_index* idx, const char* path, const int64_t* ids, int64_t n_ids);
+/* Row-sharded build: every rank of a box writes ITS rows into one index file laid out for
+ * file_total_rows rows.  The rank that owns row 0 calls first with create = 1 (header + extent),
+ * the others after it (a barrier between) with create = 0; ids = this shard's image ids or NULL
+ * on every rank alike. */
+int b2k_save_shard(b2k_index* idx, const char* path, const int64_t* ids, int64_t file_row_begin,
+                   int64_t file_total_rows, int32_t create);
 int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_end,
              b2k_index** out);
 int b2k_file_info(const char* path, int64_t* n_rows, int32_t* n_tables, int32_t* table_dims,

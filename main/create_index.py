@@ -41,6 +41,7 @@ class FAISSIndexBuilderDB:
         log_dir: str = "logs",
         device: int = 0,
         native_ingest: bool = True,
+        sharded: bool = None,
     ):
         # reference: create_index.py:14-53 (same attribute names; `device` is new)
         self.log_dir = log_dir
@@ -63,14 +64,17 @@ class FAISSIndexBuilderDB:
         self.efSearch = efSearch
         self.device = device
         self.native_ingest = native_ingest     # new: SQL -> decode -> pack loop in libb2k.so (csrc/ingest.cu)
+        # new: under torchrun (torch.distributed initialised, world > 1) every rank ingests and packs ITS row
+        # range on its own GPU and all ranks write one index file together (None = auto, False = never)
+        self.sharded = sharded
 
         self.offset_table = f"faiss_index_offsets_{name}"
 
-        self.read_conn = sqlite3.connect(self.db_path)
+        self.read_conn = sqlite3.connect(self.db_path, timeout=60)
         self._configure_db(self.read_conn)
         self.read_cur = self.read_conn.cursor()
 
-        self.write_conn = sqlite3.connect(self.db_path)
+        self.write_conn = sqlite3.connect(self.db_path, timeout=60)
         self._configure_db(self.write_conn)
         self.write_cur = self.write_conn.cursor()
 
@@ -95,7 +99,17 @@ class FAISSIndexBuilderDB:
 
     # ---- SQLite (create_index.py:89-158) ------------------------------------------------------
     def _configure_db(self, conn):
-        conn.execute("PRAGMA journal_mode=WAL;")
+        # several ranks of a sharded build open the database at once: switching the journal mode needs a
+        # moment of exclusive access and does not wait on the busy handler, so retry it
+        import time
+        for attempt in range(200):
+            try:
+                conn.execute("PRAGMA journal_mode=WAL;")
+                break
+            except sqlite3.OperationalError as e:
+                if "locked" not in str(e) or attempt == 199:
+                    raise
+                time.sleep(0.05)
         conn.execute("PRAGMA synchronous=OFF;")
 
     def _prepare_offset_table(self):
@@ -238,6 +252,81 @@ class FAISSIndexBuilderDB:
             return None, []
         return index, [int(i) for i in ids]
 
+    @staticmethod
+    def _dist_world():
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_world_size(), dist.get_rank()
+        except Exception:
+            pass
+        return 1, 0
+
+    def _build_sharded(self, world, rank):
+        """Row-sharded build (ingest shards like the search): rank r takes rows
+        [r0, r1) of the join in id order, packs them on its GPU, and all ranks write ONE index file
+        (`b2k_save_shard`) whose offsets equal those of a single-GPU build.  A database too large for one
+        GPU (BASELINE config 5: 100 M rows = 134 GB per GPU on eight) can only be built this way."""
+        import torch
+        import torch.distributed as dist
+        from image_recommender_b200 import B2KError, _capi
+        from image_recommender_b200.sharded import shard_range
+        dev = torch.device("cuda", self.device)
+        if rank == 0:
+            if self.index_file.exists():
+                self.index_file.unlink()
+            self.write_cur.execute(f"DELETE FROM {self.offset_table}")
+            self.write_conn.commit()
+        dist.barrier()
+        total = self._count_records()
+        self._log(f"[rank {rank}/{world}] {total} complete records found.", level="info")
+        if total == 0:
+            return
+        r0, r1 = shard_range(total, world, rank)
+        select_cols, join_strs = self._make_select_and_joins()
+        base_sql = f"SELECT {select_cols} FROM images i {join_strs}"
+        sql = f"{base_sql} ORDER BY i.id LIMIT {r1 - r0} OFFSET {r0}"
+        first = self.read_cur.execute(base_sql + " ORDER BY i.id LIMIT 1").fetchone()
+        dims = [int(self._decode_blob(b).shape[0]) for b in first[1:]]
+        index = self._initialize_index(dims, max(r1 - r0, 1))
+        ids = None
+        if self.native_ingest and r1 > r0:
+            try:
+                ids = [int(i) for i in index.ingest_sqlite(self.db_path, sql, r1 - r0)]
+            except B2KError as e:
+                if e.status != _capi.E_UNSUPPORTED:
+                    raise
+                self._log(f"[rank {rank}] native ingest declined ({e}); decoding in Python.", level="warning")
+                index.reset()
+        if ids is None:
+            ids = []
+            cur = self.read_conn.cursor()
+            cur.execute(sql)
+            while True:
+                rows = cur.fetchmany(self.batch_size)
+                if not rows:
+                    break
+                b_ids, parts = self._decode_batch(rows)
+                if b_ids:
+                    index.add_tables([np.stack([p[t] for p in parts]).astype("float32") for t in range(len(dims))])
+                    ids.extend(b_ids)
+        # rows skipped on decode errors shift the offsets of every later rank: exchange the counts
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        mine = torch.tensor([len(ids)], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, mine)
+        counts = counts.cpu().tolist()
+        begin, n_all = sum(counts[:rank]), sum(counts)
+        for r in range(world):            # one writer at a time: the creating rank first, SQLite one process at a time
+            if r == rank:
+                index.save_shard(self.index_file, np.asarray(ids, dtype=np.int64), begin, n_all, create=(rank == 0))
+                for lo in range(0, len(ids), self.batch_size):
+                    self._store_offsets(ids[lo:lo + self.batch_size], begin + lo)
+            dist.barrier()
+        self._log(f"[rank {rank}] wrote rows [{begin}, {begin + len(ids)}) of {n_all} to {self.index_file}", level="info")
+        index.close()
+        self.read_conn.close()
+        self.write_conn.close()
+
     def _store_offsets(self, ids, start_offset):
         pairs = [(rid, start_offset + i) for i, rid in enumerate(ids)]
         self.write_cur.executemany(
@@ -256,6 +345,11 @@ class FAISSIndexBuilderDB:
         (the reference's flag restarts at offset 0 and is unusable)."""
         combo = "_".join(self.vector_types)
         self._log(f"Starting index build for [{combo}]…", level="info")
+        world, rank = self._dist_world()
+        if world > 1 and self.sharded is not False:
+            if update_index:
+                raise ValueError("update_index is not supported for a row-sharded build")
+            return self._build_sharded(world, rank)
 
         index = None
         all_ids: list[int] = []
@@ -336,11 +430,21 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--update", action="store_true", help="append images that have no offset yet")
     a = ap.parse_args(argv)
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:       # torchrun --nproc-per-node G -m main.create_index ...: row-sharded build on G GPUs
+        import torch
+        import torch.distributed as dist
+        a.device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(a.device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", a.device))
     builder = FAISSIndexBuilderDB(
         db_path=a.db_path, vector_types=a.vector_types, batch_size=a.batch_size, index_file=a.output,
         hnsw_M=a.hnsw_M, efConstruction=a.efConstruction, efSearch=a.efSearch, device=a.device,
     )
     builder.build_index(update_index=a.update)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

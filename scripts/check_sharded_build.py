@@ -1,0 +1,51 @@
+"""torchrun check of the row-sharded build (main/create_index.py under torch.distributed): every rank ingests
+its row range on its own GPU and all write one index file; file and offset table must equal a single-GPU build.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/check_sharded_build.py"""
+import json, os, shutil, sqlite3, sys, tempfile
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import torch
+import torch.distributed as dist
+from test_ingest import _make_db
+from main.create_index import FAISSIndexBuilderDB
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+tmp = Path(tempfile.gettempdir()) / "b2k_check_sharded_build"
+res = {"world": world}
+ok = True
+for case, foreign in (("clean", None), ("foreign_blob", ("sift", 4000))):
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True); tmp.mkdir(parents=True)
+        _make_db(tmp / "images.db", 6001, seed=7, foreign_at=foreign, missing={("sift", 9), ("color", 3000), ("dreamsim", 6001)})
+    dist.barrier()
+    types = ["color", "sift", "dreamsim"]
+    b = FAISSIndexBuilderDB(db_path=str(tmp / "images.db"), vector_types=types, index_file=str(tmp / "sharded.faiss"),
+                            log_dir=str(tmp / f"logs{rank}"), batch_size=700, device=local)
+    b._log = lambda m, level="info": None
+    b.build_index()
+    dist.barrier()
+    if rank == 0:
+        conn = sqlite3.connect(tmp / "images.db")
+        tab_sh = conn.execute(f"SELECT image_id, offset FROM {b.offset_table} ORDER BY offset").fetchall()
+        conn.close()
+        s = FAISSIndexBuilderDB(db_path=str(tmp / "images.db"), vector_types=types, index_file=str(tmp / "single.faiss"),
+                                log_dir=str(tmp / "logs_single"), batch_size=700, device=local, sharded=False)
+        s._log = lambda m, level="info": None
+        s.build_index()
+        conn = sqlite3.connect(tmp / "images.db")
+        tab_1 = conn.execute(f"SELECT image_id, offset FROM {s.offset_table} ORDER BY offset").fetchall()
+        conn.close()
+        same_file = (tmp / "sharded.faiss").read_bytes() == (tmp / "single.faiss").read_bytes()
+        res[case] = {"rows": len(tab_1), "same_file": same_file, "same_offsets": tab_sh == tab_1}
+        ok = ok and same_file and tab_sh == tab_1 and len(tab_1) == 5998
+    dist.barrier()
+flag = torch.tensor([int(ok)], device="cuda")
+dist.broadcast(flag, 0)
+if rank == 0:
+    print(json.dumps(res), flush=True)
+    shutil.rmtree(tmp, ignore_errors=True)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)

@@ -678,3 +678,31 @@ def test_more_queries_than_one_pass(gpu):
     torch.cuda.synchronize()
     assert np.array_equal(ld.cpu().numpy(), lab) and np.array_equal(dd.cpu().numpy().view(np.uint32), dist.view(np.uint32))
     ix.close()
+
+
+def test_save_shard_equals_whole_save(gpu, tmp_path):
+    """b2k_save_shard: three shards written into one laid-out file (creator first) == b2k_save of the whole."""
+    irb = _irb()
+    from image_recommender_b200.sharded import shard_range
+    n = 1001
+    tabs, _ = _mk(n)
+    ids = np.arange(n, dtype=np.int64) * 7 + 3
+    whole = irb.FlatShard(DIMS, n, device=gpu)
+    whole.add_tables(tabs)
+    whole.save(tmp_path / "whole.faiss", ids)
+    for with_ids in (True, False):
+        out = tmp_path / f"sharded_{with_ids}.faiss"
+        for r in range(3):
+            r0, r1 = shard_range(n, 3, r)
+            part = irb.FlatShard(DIMS, r1 - r0, device=gpu, base_offset=r0)
+            part.add_tables([t[r0:r1] for t in tabs])
+            part.save_shard(out, ids[r0:r1] if with_ids else None, r0, n, create=(r == 0))
+            part.close()
+        if with_ids:
+            assert out.read_bytes() == (tmp_path / "whole.faiss").read_bytes()
+        else:
+            whole.save(tmp_path / "whole_noids.faiss")
+            assert out.read_bytes() == (tmp_path / "whole_noids.faiss").read_bytes()
+    with pytest.raises(irb.B2KError):        # a shard that does not fit the layout
+        whole.save_shard(tmp_path / "sharded_True.faiss", ids, 5, n, create=False)
+    whole.close()
