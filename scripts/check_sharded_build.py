@@ -42,6 +42,35 @@ for case, foreign in (("clean", None), ("foreign_blob", ("sift", 4000))):
         res[case] = {"rows": len(tab_1), "same_file": same_file, "same_offsets": tab_sh == tab_1}
         ok = ok and same_file and tab_sh == tab_1 and len(tab_1) == 5998
     dist.barrier()
+    if case == "clean":
+        # the reference-shaped query API on the sharded index: every rank loads its row range of the file just
+        # built, issues the same query, and gets the single-GPU answer
+        from main.search_from_image import ImageRecommender
+        import image_recommender_b200 as irb
+        os.chdir(tmp)
+        shutil.copy(tmp / "sharded.faiss", tmp / "index_hnsw_color_sift_dreamsim.faiss") if rank == 0 else None
+        dist.barrier()
+        rec = ImageRecommender(images_root="image_data", db_path=str(tmp / "images.db"), top_k=7, index_dir=str(tmp), device=local)
+        qpaths = [str(tmp / "image_data" / "000123.jpg"), str(tmp / "image_data" / "004321.jpg")]
+        got = [rec.search_similar_images([p], index_type="combo_color_sift_dreamsim") for p in qpaths]
+        got.append(rec.search_similar_images(qpaths, index_type="color,sift,dreamsim"))
+        mine = json.dumps([[(str(p), d) for p, d in g] for g in got])
+        alls = [None] * world
+        dist.all_gather_object(alls, mine)
+        same_on_all_ranks = all(a == alls[0] for a in alls)
+        self_first = got[0][0][0].name == "000123.jpg" and got[1][0][0].name == "004321.jpg"
+        single_ok = True
+        if rank == 0:
+            whole = irb.FlatShard.load(tmp / "single.faiss", device=local)
+            qv = rec._extract_query_vector([rec._relative(qpaths[0])], ["color", "sift", "dreamsim"])
+            d1, l1 = whole.search(qv, 7)
+            single_ok = [round(float(x), 6) for x in d1[0]] == [round(d, 6) for _, d in got[0]]
+            whole.close()
+            res["recommender"] = {"same_on_all_ranks": same_on_all_ranks, "self_first": self_first, "equals_single_gpu": single_ok,
+                                  "kind": type(next(iter(rec._resident.values()))[1]).__name__}
+        ok = ok and same_on_all_ranks and self_first and single_ok
+        rec.close()
+        dist.barrier()
 flag = torch.tensor([int(ok)], device="cuda")
 dist.broadcast(flag, 0)
 if rank == 0:
