@@ -241,7 +241,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     }
     // CTA pairs work on 256-query tiles: when the last one would be at most half full (3, 5 or 7
     // tiles of 128) the single-CTA kernel wastes no tensor work and measures 6-40 % faster
-    // (gpurun_out/exp_mid.log); from 1024 queries on the pair kernel's lower operand traffic wins.
+    // (profiles/experiments/r01_exp_mid.log); from 1024 queries on the pair kernel's lower operand traffic wins.
     const int n_qt128 = (nq + 127) / 128;
     const bool pair = ix->opt_pair < 0 ? (nq > 128 && !((n_qt128 & 1) && n_qt128 <= 7)) : ix->opt_pair != 0;
     const int forced = std::min(ix->opt_splits, w.n_lists);
@@ -260,7 +260,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     const int64_t tiles_total = (ix->ntotal + 255) / 256;
     const int64_t tiles_per_split = tiles_total / ta.plan.n_splits;
     // tiny batches on short splits: one launch without a floor beats sampling + seeding + main pass
-    // (a single live query per warp inserts without divergence; gpurun_out/exp_path.log)
+    // (a single live query per warp inserts without divergence; profiles/experiments/r01_exp_path.log)
     bool seed = ix->opt_seed && tiles_per_split >= 16 && (ix->opt_seed > 1 || nq > 4 || tiles_per_split >= 128);
     // sample ~0.75 % of the shard whatever the split count: a smaller sample leaves the floor too low
     // (more list insertions in the main pass), a larger one costs more than it saves

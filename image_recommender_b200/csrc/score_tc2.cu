@@ -174,7 +174,7 @@ ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, 
   // CTA pays one pipeline fill + one un-overlapped last epilogue (about 1.5 tile times).  With >= 128
   // tiles per CTA that is noise and more, shorter CTAs balance better (10 M rows: 148 splits best);
   // on small shards fewer splits win (1.25 M rows: 37 instead of 148 splits is +8 % at batch 4096,
-  // +10 % at batch 512; gpurun_out/exp_splits.log).  Only split counts that keep
+  // +10 % at batch 512; profiles/experiments/r01_exp_splits.log).  Only split counts that keep
   // n_qtiles * n_splits a whole number of waves are considered.
   int splits = n_sm;
   if (forced_splits > 0) {
