@@ -169,7 +169,7 @@ def cpu_baseline(rows: int, batch: int, k: int, reps: int = 1):
     import numpy as np
     import oracle
     from oracle import cpu_flat
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_host_threads()
     tabs = oracle.synth_rows(DIMS, rows, total_rows=rows)
     db = oracle.pack(tabs)["f32"]
     del tabs
@@ -212,6 +212,17 @@ def hnsw_baseline(rows: int, k: int, nq: int = 1000):
     return out
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank: give the CPU arm back all the cores it may use."""
+    cores = len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    return cores
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this metric.  faiss_cpu is not
     installable here, so this is the oracle port (kind 'port') on a bounded sample."""
@@ -223,7 +234,7 @@ def run_reference(args):
     import numpy as np
     import oracle
     from oracle import cpu_flat
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_host_threads()
     tabs = oracle.synth_rows(DIMS, rows, total_rows=rows)
     db = oracle.pack(tabs)["f32"]
     del tabs
