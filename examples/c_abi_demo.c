@@ -91,7 +91,7 @@ int main(int argc, char** argv) {
   const char* path = "/tmp/b2k_c_abi_demo.faiss";
   CHECK(b2k_save(ix, path, NULL, 0));
   b2k_index* back = NULL;
-  CHECK(b2k_load(path, 0, 0, -1, &back));
+  CHECK(b2k_load(path, 0, 0, -1, 0, &back));
   float* dist2 = (float*)malloc(sizeof(float) * (size_t)nq * k);
   int64_t* lab2 = (int64_t*)malloc(sizeof(int64_t) * (size_t)nq * k);
   CHECK(b2k_search(back, q, nq, k, dist2, lab2, NULL));

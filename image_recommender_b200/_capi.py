@@ -17,7 +17,7 @@ B2K_LIST = 32
 
 OPT_PATH, OPT_RERANK, OPT_FORCE_EXACT, OPT_SCAN_MAX_B, OPT_SPLITS, OPT_TC_PAIR, OPT_SEED, OPT_TIGHTEN, OPT_COLLECT, OPT_INLINE_SEED = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 PATH_AUTO, PATH_SCAN, PATH_TC = 0, 1, 2
-E_INVALID, E_CAPACITY, E_IO, E_NODEVICE, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
+E_INVALID, E_CAPACITY, E_IO, E_NODEVICE, E_NOMEM, E_UNSUPPORTED, E_PEER = -1, -2, -3, -4, -5, -6, -7
 
 
 class B2KError(RuntimeError):
@@ -27,11 +27,11 @@ class B2KError(RuntimeError):
 
 
 class Stats(C.Structure):
-    _fields_ = [("path", C.c_int32), ("n_splits", C.c_int32), ("n_rerank", C.c_int32),
+    _fields_ = [("path", C.c_int32), ("n_splits", C.c_int32), ("cand_slots", C.c_int32),
                 ("n_uncertified", C.c_int32), ("eps_max", C.c_float), ("err_max", C.c_float),
                 ("norm_max", C.c_float), ("launches", C.c_int32), ("score_ms", C.c_float),
                 ("tail_ms", C.c_float), ("n_queries", C.c_int32), ("n_candidates", C.c_int32),
-                ("n_saturated", C.c_int32)]
+                ("n_saturated", C.c_int32), ("n_timed", C.c_int32)]
 
 
 class Synth(C.Structure):
@@ -81,10 +81,11 @@ SIGNATURES = {
     "b2k_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2k_xchg_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b2k_xchg_merge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2k_xchg_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "b2k_normalize_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "b2k_save": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "b2k_save_shard": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
-    "b2k_load": (C.c_int, [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
+    "b2k_load": (C.c_int, [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
     "b2k_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b2k_load_ids": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p]),

@@ -1,8 +1,11 @@
 // C ABI of the b2k engine (include/b2k.h): index object, build (add), search pipeline,
 // persistence and the synthetic-data helpers.  Host side only; kernels live in pack.cu,
 // scan.cu, score_tc.cu and select.cu.
+#define _FILE_OFFSET_BITS 64      // fseeko/off_t are 64-bit whatever the ABI's `long` is
 #include <cuda.h>
 #include <stdarg.h>
+#include <stdio.h>
+#include <sys/types.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -28,6 +31,7 @@ namespace {
 constexpr int64_t kMaxStageRows = 65536;  // rows per staging chunk of add() / load() / fill_synthetic() (fewer for very wide rows)
 constexpr int kMaxNqPerPass = 16384;      // queries per pipeline pass (workspace sizing)
 constexpr int kDefaultCandCap = 0;      // 0: every listed entry can be a candidate (no overflow)
+constexpr int kEvRing = 64;             // pipeline passes whose device times b2k_get_stats can average
 
 struct DeviceGuard {
   int prev = -1;
@@ -104,6 +108,7 @@ struct b2k_index {
   alignas(64) CUtensorMap tmap_q, tmap_db, tmap_db2;   // tmap_db2: 128-row boxes for the CTA-pair kernel
   const void* tmap_q_ptr = nullptr; int tmap_q_rows = 0;
   const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
+  int coresident[2] = {-1, -1};               // CTAs of score_tc / score_tc2 resident at once (occupancy query, lazily)
   int opt_pair = -1;                          // -1 auto (nq > 128), 0 never, 1 always
   int opt_seed = 1;                           // threshold seeding for the tcgen05 paths
   int opt_tighten = 1;                        // exact-score tightening of the candidate threshold
@@ -113,8 +118,11 @@ struct b2k_index {
   int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 0, opt_splits = 0;
   b2k_stats stats;
   int32_t* h_fail = nullptr;                  // pinned
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // before scoring, after scoring, after the tail
-  bool ev_valid = false;
+  // timing: a ring of (before scoring, after scoring, after the tail) event triples, one per pipeline pass, so
+  // that back-to-back searches can be timed kernel by kernel without a host sync in between (b2k_get_stats
+  // averages the passes recorded since the previous b2k_get_stats)
+  cudaEvent_t ev[kEvRing][3] = {{nullptr}};
+  int64_t ev_head = 0, ev_read = 0;           // passes recorded / passes already reported
 };
 
 namespace {
@@ -214,7 +222,8 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
 
   int n_lists_used = 0, split_tile_rows = 0;
   const float* eps = nullptr;
-  B2K_CUDA(cudaEventRecord(ix->ev[0], st));
+  cudaEvent_t* ev = ix->ev[ix->ev_head % kEvRing];
+  B2K_CUDA(cudaEventRecord(ev[0], st));
   if (path == 1) {
     ScanArgs sa;
     sa.db = ix->bf16; sa.n_rows = ix->ntotal; sa.D = ix->D; sa.Dp = ix->Dp; sa.q = q_dev; sa.nq = nq;
@@ -269,9 +278,13 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // One query tile on the single-CTA kernel = one resident CTA per split: the sampling pass, the seed
     // kernel and the re-read of the sampled tiles fold into the main launch (in-kernel seeding).
     // (CTA pairs: up to 256 queries when the pairs of one query tile fill at most one wave.)
+    // The grid barrier needs every CTA resident: the grid must fit what the occupancy query says this device
+    // holds at once (the barrier itself is bounded in time should that still fail at run time).
     const int n_ctas = pair ? 2 * ta.plan.n_splits : ta.plan.n_splits;
+    int& resident = ix->coresident[pair ? 1 : 0];
+    if (resident < 0) resident = pair ? score_tc2_max_coresident(ix->n_sm) : score_tc_max_coresident(ix->n_sm);
     if (seed && ix->opt_inline_seed && ix->opt_seed == 1 && k <= kList && ta.plan.n_qtiles == 1 &&
-        n_ctas <= ix->n_sm && ta.plan.n_splits <= 160 && nq <= (pair ? 2 : 1) * n_ctas) {
+        n_ctas <= resident && ta.plan.n_splits <= 160 && nq <= (pair ? 2 : 1) * n_ctas) {
       ta.seed_k = k;
       seed = false;
     }
@@ -295,7 +308,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     split_tile_rows = score_tc_tile_rows();
     eps = w.eps_tc;
   }
-  B2K_CUDA(cudaEventRecord(ix->ev[1], st));
+  B2K_CUDA(cudaEventRecord(ev[1], st));
   // the select kernel reads lists [0, n_lists_used) of the stride-n_lists layout
   SelectArgs se;
   se.partial = w.partial; se.n_lists = n_lists_used; se.list_stride = w.n_lists; se.k = k; se.eps = eps;
@@ -352,14 +365,14 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     if (rc) return rc;
     launches += 2;
   }
-  B2K_CUDA(cudaEventRecord(ix->ev[2], st));
-  ix->ev_valid = true;
+  B2K_CUDA(cudaEventRecord(ev[2], st));
+  ix->ev_head += 1;
 
   ix->stats.path = path;
   ix->stats.n_queries = nq;
   ix->stats.n_uncertified = -1;      // on the device until read back
   ix->stats.n_splits = n_lists_used;
-  ix->stats.n_rerank = w.cand_cap;
+  ix->stats.cand_slots = w.cand_cap;
   ix->stats.launches = launches;
   return 0;
 }
@@ -449,8 +462,8 @@ int b2k_create(const int32_t* table_dims, int32_t n_tables, int64_t capacity_row
   if (!rc) rc = dev_alloc(&ix->stat_bits, 2);
   if (!rc && (e = cudaMemset(ix->stat_bits, 0, 2 * sizeof(unsigned int))) != cudaSuccess) rc = (int)e;
   if (!rc && (e = cudaMallocHost(reinterpret_cast<void**>(&ix->h_fail), 64)) != cudaSuccess) rc = (int)e;
-  for (int i = 0; i < 3 && !rc; ++i)
-    if ((e = cudaEventCreate(&ix->ev[i])) != cudaSuccess) rc = (int)e;
+  for (int i = 0; i < kEvRing * 3 && !rc; ++i)
+    if ((e = cudaEventCreate(&ix->ev[i / 3][i % 3])) != cudaSuccess) rc = (int)e;
   if (rc) {
     if (rc > 0) set_error("create: %s (capacity %lld rows x %d dims)", cudaGetErrorString((cudaError_t)rc),
                           (long long)capacity_rows, ix->D);
@@ -472,7 +485,7 @@ void b2k_destroy(b2k_index* ix) {
   dev_free(ix->stage_rows_f32);
   b2k_stage_close(ix);
   if (ix->h_fail) cudaFreeHost(ix->h_fail);
-  for (int i = 0; i < 3; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+  for (int i = 0; i < kEvRing * 3; ++i) if (ix->ev[i / 3][i % 3]) cudaEventDestroy(ix->ev[i / 3][i % 3]);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -721,11 +734,22 @@ int b2k_get_stats(b2k_index* ix, b2k_stats* out) {
     for (int32_t c : cnt) tot += std::min(c, ix->ws.cand_cap);
     ix->stats.n_candidates = (int32_t)std::min<int64_t>(tot, 0x7fffffff);
   }
-  if (ix->ev_valid) {
-    float a = 0.f, b = 0.f;
-    if (cudaEventElapsedTime(&a, ix->ev[0], ix->ev[1]) == cudaSuccess) ix->stats.score_ms = a;
-    if (cudaEventElapsedTime(&b, ix->ev[1], ix->ev[2]) == cudaSuccess) ix->stats.tail_ms = b;
+  if (ix->ev_head > ix->ev_read) {
+    // mean over the passes recorded since the last call (at most the ring's depth, the most recent ones)
+    const int64_t first = std::max(ix->ev_read, ix->ev_head - kEvRing);
+    double sa = 0.0, sb = 0.0;
+    int n = 0;
+    for (int64_t i = first; i < ix->ev_head; ++i) {
+      float a = 0.f, b = 0.f;
+      cudaEvent_t* ev = ix->ev[i % kEvRing];
+      if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess && cudaEventElapsedTime(&b, ev[1], ev[2]) == cudaSuccess) {
+        sa += a; sb += b; ++n;
+      }
+    }
     cudaGetLastError();
+    if (n > 0) { ix->stats.score_ms = (float)(sa / n); ix->stats.tail_ms = (float)(sb / n); }
+    ix->stats.n_timed = n;
+    ix->ev_read = ix->ev_head;
   }
   *out = ix->stats;
   return 0;
@@ -811,7 +835,7 @@ int write_shard_rows(b2k_index* ix, FILE* f, const char* path, const int64_t* id
                      int64_t file_total_rows) {
   const int64_t rows_offset = sizeof(FileHeader);
   const int64_t ids_offset = rows_offset + file_total_rows * (int64_t)ix->D * 4;
-  bool ok = fseek(f, (long)(rows_offset + file_row_begin * (int64_t)ix->D * 4), SEEK_SET) == 0;
+  bool ok = fseeko(f, (off_t)(rows_offset + file_row_begin * (int64_t)ix->D * 4), SEEK_SET) == 0;
   const int64_t chunk = std::max<int64_t>(256, std::min<int64_t>(ix->stage_rows, ((int64_t)1 << 26) / ((int64_t)ix->D * 4)));
   float* pin[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -837,7 +861,7 @@ int write_shard_rows(b2k_index* ix, FILE* f, const char* path, const int64_t* id
   for (int s = 0; s < 2; ++s) { if (pin[s]) cudaFreeHost(pin[s]); if (ev[s]) cudaEventDestroy(ev[s]); }
   if (e != cudaSuccess) { set_error("save: %s", cudaGetErrorString(e)); return (int)e; }
   if (ok && ids && ix->ntotal > 0)
-    ok = fseek(f, (long)(ids_offset + file_row_begin * 8), SEEK_SET) == 0 &&
+    ok = fseeko(f, (off_t)(ids_offset + file_row_begin * 8), SEEK_SET) == 0 &&
          fwrite(ids, 8, (size_t)ix->ntotal, f) == (size_t)ix->ntotal;
   if (!ok) { set_error("save: write to %s failed", path); return B2K_E_IO; }
   return 0;
@@ -887,7 +911,7 @@ int b2k_save_shard(b2k_index* ix, const char* path, const int64_t* ids, int64_t 
     FileHeader h;
     fill_header(ix, h, file_total_rows, ids != nullptr);
     const int64_t size = h.ids_offset + (ids ? file_total_rows * 8 : 0);
-    if (fwrite(&h, sizeof(h), 1, f) != 1 || (size > (int64_t)sizeof(h) && (fseek(f, (long)(size - 1), SEEK_SET) != 0 || fputc(0, f) == EOF))) {
+    if (fwrite(&h, sizeof(h), 1, f) != 1 || (size > (int64_t)sizeof(h) && (fseeko(f, (off_t)(size - 1), SEEK_SET) != 0 || fputc(0, f) == EOF))) {
       set_error("save_shard: cannot lay out %s", path);
       rc = B2K_E_IO;
     }
@@ -926,13 +950,14 @@ int b2k_load_ids(const char* path, int64_t row_begin, int64_t n, int64_t* ids_ou
   FileHeader h;
   int rc = read_header(f, h, path);
   if (!rc && (!h.has_ids || row_begin + n > h.n_rows)) { set_error("load_ids: %s holds no ids for that range", path); rc = B2K_E_IO; }
-  if (!rc && (fseek(f, (long)(h.ids_offset + row_begin * 8), SEEK_SET) != 0 ||
+  if (!rc && (fseeko(f, (off_t)(h.ids_offset + row_begin * 8), SEEK_SET) != 0 ||
               fread(ids_out, 8, (size_t)n, f) != (size_t)n)) { set_error("load_ids: short read"); rc = B2K_E_IO; }
   fclose(f);
   return rc;
 }
 
-int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_end, b2k_index** out) {
+int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_end, int64_t capacity_rows,
+             b2k_index** out) {
   if (!path || !out) { set_error("load: bad argument"); return B2K_E_INVALID; }
   *out = nullptr;
   FILE* f = fopen(path, "rb");
@@ -944,7 +969,7 @@ int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_en
   if (row_begin < 0 || row_begin > row_end) { fclose(f); set_error("load: bad row range"); return B2K_E_INVALID; }
   const int64_t n = row_end - row_begin;
   b2k_index* ix = nullptr;
-  rc = b2k_create(h.dims, h.n_tables, n, device, row_begin, &ix);
+  rc = b2k_create(h.dims, h.n_tables, std::max(n, capacity_rows), device, row_begin, &ix);
   if (rc) { fclose(f); return rc; }
   if (ix->D != h.D) { fclose(f); b2k_destroy(ix); set_error("load: corrupt header"); return B2K_E_IO; }
   DeviceGuard g(device);
@@ -960,7 +985,7 @@ int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_en
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("load: %s", cudaGetErrorString(e)); rc = (int)e; }
   }
-  if (!rc && fseek(f, (long)(h.rows_offset + row_begin * (int64_t)ix->D * 4), SEEK_SET) != 0) { set_error("load: seek failed"); rc = B2K_E_IO; }
+  if (!rc && fseeko(f, (off_t)(h.rows_offset + row_begin * (int64_t)ix->D * 4), SEEK_SET) != 0) { set_error("load: seek failed"); rc = B2K_E_IO; }
   int slot = 0;
   for (int64_t r0 = 0; !rc && r0 < n; r0 += chunk, slot ^= 1) {
     const int64_t m = std::min(chunk, n - r0);

@@ -181,9 +181,14 @@ __device__ __forceinline__ double lane_dot64_qd(const double* __restrict__ qd, c
 // G-way merge (G <= 32) of per-shard result lists, each already in the global order (higher ip, then
 // lower offset) with label < 0 padding at its end: one warp per query, lane g walks list g, every
 // step is one warp arg-best.  O(k log G) for any k.  addr(g, j) = flat index of entry j of list g.
-template <typename Addr>
-__device__ __forceinline__ void warp_merge_sorted(const float* __restrict__ ip, const float* __restrict__ dist,
-                                                  const int64_t* __restrict__ lab, Addr addr, int G, int k, int lane,
+// kCoherent: the lists were written by OTHER GPUs during this kernel (K-exchange): every read goes to L2
+// (ld.global.cg) — never through the non-coherent path a const __restrict__ pointer permits.
+template <bool kCoherent, typename T>
+__device__ __forceinline__ T merge_ld(const T* p) { return kCoherent ? __ldcg(p) : *p; }
+
+template <bool kCoherent = false, typename Addr>
+__device__ __forceinline__ void warp_merge_sorted(const float* ip, const float* dist,
+                                                  const int64_t* lab, Addr addr, int G, int k, int lane,
                                                   float* out_ip, float* out_dist, int64_t* out_lab) {
   int h = 0;
   uint32_t key = 0u;
@@ -193,9 +198,9 @@ __device__ __forceinline__ void warp_merge_sorted(const float* __restrict__ ip, 
     valid = lane < G && h < k;
     if (valid) {
       src = addr(lane, h);
-      off = lab[src];
+      off = merge_ld<kCoherent>(lab + src);
       valid = off >= 0;
-      if (valid) key = float_key(ip[src]);
+      if (valid) key = float_key(merge_ld<kCoherent>(ip + src));
     }
   };
   load();
@@ -220,8 +225,8 @@ __device__ __forceinline__ void warp_merge_sorted(const float* __restrict__ ip, 
       continue;
     }
     if (lane == bl) {
-      if (out_ip) out_ip[j] = ip[src];
-      out_dist[j] = dist[src];
+      if (out_ip) out_ip[j] = merge_ld<kCoherent>(ip + src);
+      out_dist[j] = merge_ld<kCoherent>(dist + src);
       out_lab[j] = off;
       ++h;
       load();
@@ -257,7 +262,7 @@ __device__ __forceinline__ float bf16_bits_to_f32(uint16_t h) {
 
 // ---------------------------------------------------------------------------------------
 // Synthetic generator (Spec G) — integer hashing + exact int->float steps only, so that
-// oracle/synth.py reproduces every bit on the CPU.
+// oracle/b2k_oracle.c (orc_synth_rows) reproduces every bit on the CPU.
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

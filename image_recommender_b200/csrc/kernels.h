@@ -207,6 +207,8 @@ ScoreTcPlan score_tc_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, i
 int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_bf16, int nq_pad,
                          const uint16_t* db_bf16, int64_t n_rows, int Dp);
 int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st);
+int score_tc_max_coresident(int n_sm);    // CTAs resident at once (occupancy query): bound of the in-kernel seeding
+int score_tc2_max_coresident(int n_sm);
 // CTA-pair variant (score_tc2.cu): 256 queries per pair, DB tile halves of 128 rows per CTA
 ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, int min_splits);
 int score_tc2_encode_db_map(void* tmap_db_out, const uint16_t* db_bf16, int64_t n_rows, int Dp);

@@ -177,7 +177,7 @@ query_prep_kernel(QueryPrepArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Synthetic rows (Spec G, mirrored by oracle/synth.py): raw (un-normalised) per-table fp32.
+// Synthetic rows (Spec G, mirrored by oracle/b2k_oracle.c: orc_synth_rows): raw (un-normalised) per-table fp32.
 __device__ __forceinline__ uint64_t h2(uint64_t a, uint64_t b) { return mix64(mix64(a) ^ b); }
 
 __global__ void __launch_bounds__(256)

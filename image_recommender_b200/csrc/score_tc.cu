@@ -99,30 +99,37 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    int it = 0;
+    // every address below derives from warp-uniform bases, so ptxas keeps descriptors and barrier
+    // addresses in uniform registers (no R2UR/ELECT waterfall around each UTCHMMA / UTCBAR)
+    const uint32_t ring_u = __shfl_sync(0xffffffffu, ptx::smem_u32(ring), 0);
+    const uint32_t full_u = __shfl_sync(0xffffffffu, ptx::smem_u32(full), 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t empty_u = full_u + kStages * 8, tfull_u = empty_u + kStages * 8, tempty_u = tfull_u + 16;
+    const uint64_t desc0 = make_sw128_desc(ring_u);                     // stage s: + s * (kStageBytes >> 4)
+    int s = 0;
+    uint32_t ph = 0;                                                    // parity of the ring pass
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
-      ptx::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
+      ptx::mbar_wait_a(tempty_u + acc * 8, ((t >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBlockN);
-      for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
-        const int s = it % kStages;
-        ptx::mbar_wait(&full[s], (it / kStages) & 1);
+      const uint32_t d_tmem = tmem_u + (uint32_t)(acc * kBlockN);
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        ptx::mbar_wait_a(full_u + s * 8, ph);
         ptx::tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * kStageBytes);
-          const uint64_t a_desc = make_sw128_desc(a_addr);
-          const uint64_t b_desc = make_sw128_desc(a_addr + kABytes);
+          const uint64_t a_desc = desc0 + (uint64_t)(s * (kStageBytes >> 4));
+          const uint64_t b_desc = a_desc + (uint64_t)(kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 32 bytes (16 bf16) inside the swizzled row: +2 in 16-byte units
             ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc,
                            (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
-          if (kb == n_kblocks - 1) ptx::umma_commit(&tfull[acc]);   // accumulator complete
+          ptx::umma_commit_a(empty_u + s * 8);                 // frees the smem stage when the MMAs retire
+          if (kb == n_kblocks - 1) ptx::umma_commit_a(tfull_u + acc * 8);   // accumulator complete
         }
         __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -243,6 +250,18 @@ int score_tc_encode_maps(void* tmap_q_out, void* tmap_db_out, const uint16_t* q_
     if (rc) return rc;
   }
   return 0;
+}
+
+// CTAs of this kernel that can be resident at once on the current device (occupancy query): the in-kernel
+// seeding's grid barrier is only enabled for grids within it.
+int score_tc_max_coresident(int n_sm) {
+  int per_sm = 0;
+  if (cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_tc_kernel, kThreads, kSmemBytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return per_sm * n_sm;
 }
 
 int launch_score_tc(const ScoreTcArgs& a, cudaStream_t st) {

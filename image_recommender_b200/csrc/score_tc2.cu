@@ -92,28 +92,35 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader only) ------------------------------
     if (rank == 0) {
-      int it = 0;
+      // every address below derives from warp-uniform bases, so ptxas keeps descriptors and barrier
+      // addresses in uniform registers (no R2UR/ELECT waterfall around each UTCHMMA / UTCBAR)
+      const uint32_t ring_u = __shfl_sync(0xffffffffu, ptx::smem_u32(ring), 0);
+      const uint32_t full_u = __shfl_sync(0xffffffffu, ptx::smem_u32(full), 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t empty_u = full_u + kStages2 * 8, tfull_u = empty_u + kStages2 * 8, tempty_u = tfull_u + 16;
+      const uint64_t desc0 = make_sw128_desc(ring_u);                   // stage s: + s * (kStageBytes2 >> 4)
+      int s = 0;
+      uint32_t ph = 0;                                                  // parity of the ring pass
       for (int t = 0; t < n_tiles; ++t) {
         const int acc = t & 1;
-        ptx::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
+        ptx::mbar_wait_a(tempty_u + acc * 8, ((t >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBlockN);
-        for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
-          const int s = it % kStages2;
-          ptx::mbar_wait(&full[s], (it / kStages2) & 1);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * kBlockN);
+        for (int kb = 0; kb < n_kblocks; ++kb) {
+          ptx::mbar_wait_a(full_u + s * 8, ph);
           ptx::tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * kStageBytes2);
-            const uint64_t a_desc = make_sw128_desc(a_addr);
-            const uint64_t b_desc = make_sw128_desc(a_addr + kABytes2);
+            const uint64_t a_desc = desc0 + (uint64_t)(s * (kStageBytes2 >> 4));
+            const uint64_t b_desc = a_desc + (uint64_t)(kABytes2 >> 4);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               ptx::umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc2,
                                   (kb | k) != 0 ? 1u : 0u);
-            ptx::umma_commit_pair(&empty[s], 3);                        // stage free in both CTAs
-            if (kb == n_kblocks - 1) ptx::umma_commit_pair(&tfull[acc], 3);   // accumulators ready in both
+            ptx::umma_commit_pair_a(empty_u + s * 8, 3);                        // stage free in both CTAs
+            if (kb == n_kblocks - 1) ptx::umma_commit_pair_a(tfull_u + acc * 8, 3);   // accumulators ready in both
           }
           __syncwarp();
+          if (++s == kStages2) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -197,6 +204,25 @@ ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, 
 
 int score_tc2_encode_db_map(void* tmap_db_out, const uint16_t* db_bf16, int64_t n_rows, int Dp) {
   return encode_2d(reinterpret_cast<CUtensorMap*>(tmap_db_out), db_bf16, (uint64_t)n_rows, (uint64_t)Dp, kBHalfRows);
+}
+
+// CTAs (2 per cluster) of this kernel that can be resident at once on the current device.
+int score_tc2_max_coresident(int n_sm) {
+  int clusters = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)n_sm, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes2;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  if (cudaFuncSetAttribute(score_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&clusters, score_tc2_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return 2 * clusters;
 }
 
 int launch_score_tc2(const ScoreTcArgs& a, cudaStream_t st) {

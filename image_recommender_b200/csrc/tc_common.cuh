@@ -221,17 +221,29 @@ __device__ __forceinline__ void list_store(uint32_t s_addr, uint32_t r_addr, Can
 // measured slower: the tiles scored meanwhile insert against an unseeded threshold.)
 constexpr int kSeedKeysPerThread = 40;        // 128 epilogue threads x 40 >= 160 lists x 32 entries
 
-// Counter barrier across the (co-resident) CTAs of the grid: 1 = everyone arrived, 0 = gave up.
+// Counter barrier across the CTAs of the grid: 1 = everyone arrived, 0 = gave up.  The launcher only enables
+// the in-kernel seeding for grids that fit the device in one wave (occupancy query, api.cu), but co-residency
+// can still fail at run time (another stream or process holding SMs, a profiler serialising CTAs): the wait is
+// therefore bounded by WALL TIME (kGridBarrierTimeoutNs on %globaltimer), after which the CTA gives up and just
+// keeps its own threshold — correctness never depends on the barrier, and the worst case costs a fraction of a
+// millisecond per search instead of stalling it (all CTAs arrive within ~10 us in the normal case).
+constexpr unsigned long long kGridBarrierTimeoutNs = 200000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t grid_barrier_arrive_wait(unsigned int* ctr, unsigned int n) {
   __threadfence();
   atomicAdd(ctr, 1u);
-  for (unsigned int spins = 0; spins < (1u << 21); ++spins) {
+  const unsigned long long t0 = global_timer_ns();
+  for (;;) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= n) return 1u;
+    if (global_timer_ns() - t0 > kGridBarrierTimeoutNs) return 0u;
     __nanosleep(40);
   }
-  return 0u;
 }
 
 // scratch: 12 u32; topk: 4 x 32 u64 of shared memory private to the epilogue warps (named barrier 2).

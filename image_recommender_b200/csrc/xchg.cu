@@ -61,29 +61,51 @@ xchg_push_kernel(XchgPeers peers, XchgLayout lay, int rank, int parity, unsigned
   }
 }
 
-// Wait for all ranks' records of this epoch, then merge.  One warp per query.
+// Wait for all ranks' records of this epoch, then merge.  One warp per query.  `mine` is written by the peers
+// over NVLink while this kernel may already be spinning: no const/__restrict__ on it, and the records are read
+// with L2-coherent loads after the acquire.  A peer that does not show up within kXchgTimeoutNs (a dead or
+// stalled rank) must neither hang this GPU nor kill its context (the resident index lives in it): the kernel
+// reports the timeout in *status, pads its outputs faiss-style (label -1) and returns; the host raises.
+constexpr unsigned long long kXchgTimeoutNs = 10000000000ull;      // 10 s
+
 __global__ void __launch_bounds__(128)
-xchg_merge_kernel(const unsigned char* __restrict__ mine, XchgLayout lay, int parity, unsigned long long epoch,
+xchg_merge_kernel(unsigned char* mine, XchgLayout lay, int parity, unsigned long long epoch,
                   int nq, int k, float* __restrict__ out_ip, float* __restrict__ out_dist,
-                  int64_t* __restrict__ out_labels) {
+                  int64_t* __restrict__ out_labels, unsigned int* status) {
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0;
+  __syncthreads();
   if (threadIdx.x < lay.world) {
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + lay.flag_off(parity, threadIdx.x));
-    unsigned long long v = 0;
-    unsigned int spins = 0;
-    do {
+    unsigned long long v = 0, t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (unsigned int spins = 0;; ++spins) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-      if (++spins > (1u << 28)) __trap();       // a dead peer must not hang this GPU forever
-    } while (v < epoch);
+      if (v >= epoch) break;
+      if ((spins & 1023u) == 1023u) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > kXchgTimeoutNs) { s_timeout = 1; atomicOr(status, 1u << threadIdx.x); break; }
+      }
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
+  if (s_timeout) {
+    for (int j = lane; j < k; j += 32) {
+      if (out_ip) out_ip[(int64_t)q * k + j] = -3.402823466e38f;
+      out_dist[(int64_t)q * k + j] = 3.402823466e38f;
+      out_labels[(int64_t)q * k + j] = -1;
+    }
+    return;
+  }
   const float* ip = reinterpret_cast<const float*>(mine + lay.ip_off(parity, 0));
   const float* dist = reinterpret_cast<const float*>(mine + lay.dist_off(parity, 0));
   const int64_t* lab = reinterpret_cast<const int64_t*>(mine + lay.lab_off(parity, 0));
   const int64_t cap = lay.cap;
-  warp_merge_sorted(ip, dist, lab, [=](int g, int j) { return (int64_t)g * cap + (int64_t)q * k + j; }, lay.world, k, lane,
+  warp_merge_sorted<true>(ip, dist, lab, [=](int g, int j) { return (int64_t)g * cap + (int64_t)q * k + j; }, lay.world, k, lane,
                     out_ip ? out_ip + (int64_t)q * k : nullptr, out_dist + (int64_t)q * k, out_labels + (int64_t)q * k);
 }
 
@@ -97,7 +119,7 @@ struct b2k_xchg {
   unsigned char* mine = nullptr;
   XchgPeers peers;
   bool opened[16] = {false};
-  unsigned int* done_ctas = nullptr;
+  unsigned int* done_ctas = nullptr;      // [0] push: finished CTAs; [1] merge: bit g set = rank g timed out
   unsigned long long epoch = 0;
   bool connected = false;
 };
@@ -119,8 +141,8 @@ int b2k_xchg_create(int32_t device, int32_t rank, int32_t world, int64_t max_ent
   x->lay.cap = max_entries; x->lay.world = world;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&x->mine), x->lay.bytes());
   if (e == cudaSuccess) e = cudaMemset(x->mine, 0, x->lay.bytes());
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->done_ctas), sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(x->done_ctas, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->done_ctas), 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(x->done_ctas, 0, 2 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     set_error("xchg_create: %s", cudaGetErrorString(e));
@@ -221,9 +243,23 @@ int b2k_xchg_merge(b2k_xchg* x, int32_t nq, int32_t k, float* out_ip, float* out
   B2K_CUDA(cudaSetDevice(x->device));
   const int parity = (int)(x->epoch & 1ull);
   xchg_merge_kernel<<<(nq + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x->mine, x->lay, parity, x->epoch, nq, k, out_ip,
-                                                                  out_dist, out_labels);
+                                                                  out_dist, out_labels, x->done_ctas + 1);
   B2K_CHECK_LAUNCH();
   if (prev >= 0) cudaSetDevice(prev);
+  return 0;
+}
+
+int b2k_xchg_status(b2k_xchg* x, uint32_t* timed_out_ranks) {
+  if (!x || !timed_out_ranks) { set_error("xchg_status: bad argument"); return B2K_E_INVALID; }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  B2K_CUDA(cudaSetDevice(x->device));
+  unsigned int v = 0;
+  B2K_CUDA(cudaMemcpy(&v, x->done_ctas + 1, sizeof(v), cudaMemcpyDeviceToHost));   // synchronises the device
+  if (v) B2K_CUDA(cudaMemset(x->done_ctas + 1, 0, sizeof(v)));
+  *timed_out_ranks = v;
+  if (prev >= 0) cudaSetDevice(prev);
+  if (v) { set_error("xchg: ranks 0x%x did not publish their top-k within 10 s (results were padded with -1)", v); return B2K_E_PEER; }
   return 0;
 }
 

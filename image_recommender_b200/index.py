@@ -123,7 +123,12 @@ class FlatShard:
         if any(t.shape[0] != n for t in tabs):
             raise ValueError("add_tables: tables disagree on the row count")
         if self.ntotal + n > self.capacity:
-            self.reserve(max(self.ntotal + n, 2 * self.capacity, 1024))
+            # amortised doubling while it fits; a shard that already fills most of the GPU grows to exactly what
+            # is needed instead (the re-allocation holds the old and the new arrays at once)
+            try:
+                self.reserve(max(self.ntotal + n, 2 * self.capacity, 1024))
+            except B2KError:
+                self.reserve(self.ntotal + n)
         ptrs = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
         check(_lib.b2k_add(self._h, ptrs, n))
 
@@ -223,10 +228,11 @@ class FlatShard:
                                   int(file_row_begin), int(file_total_rows), 1 if create else 0))
 
     @classmethod
-    def load(cls, path: str, device: int = 0, row_begin: int = 0, row_end: int = -1) -> "FlatShard":
+    def load(cls, path: str, device: int = 0, row_begin: int = 0, row_end: int = -1, capacity: int = 0) -> "FlatShard":
+        """capacity: rows to allocate for (an index about to grow is loaded into its final size: no realloc)."""
         info = file_info(path)
         h = C.c_void_p()
-        check(_lib.b2k_load(str(path).encode(), int(device), int(row_begin), int(row_end), C.byref(h)))
+        check(_lib.b2k_load(str(path).encode(), int(device), int(row_begin), int(row_end), int(capacity), C.byref(h)))
         return cls(info["table_dims"], 0, device=device, _handle=h.value)
 
     # ---- synthetic data (bench / tests) -------------------------------------------------------

@@ -72,6 +72,12 @@ class PeerExchange:
                                                   self._C.c_void_p(st)))
         return o_d, o_l, o_ip
 
+    def check(self) -> None:
+        """Synchronises the device; raises B2KError(E_PEER) if a merge since the last call gave up waiting for a
+        rank (its outputs were padded with label -1)."""
+        bits = self._C.c_uint32(0)
+        self._capi.check(self._lib.b2k_xchg_status(self._h, self._C.byref(bits)))
+
     def close(self) -> None:
         if self._h:
             self._lib.b2k_xchg_destroy(self._h)
@@ -194,6 +200,8 @@ class ShardedIndex:
                 d_, l_, _ = self._searcher.search_device(qd, k)
                 dist_out[lo:lo + step] = d_.cpu().numpy()
                 lab_out[lo:lo + step] = l_.cpu().numpy()
+        if self.exchange is not None:
+            self.exchange.check()       # a rank that never published -> B2KError instead of -1 labels
         return dist_out, lab_out
 
     def close(self) -> None:

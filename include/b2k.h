@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B2K_ABI_VERSION 1
+#define B2K_ABI_VERSION 2
 #define B2K_MAX_TABLES 8
 #define B2K_MAX_K 1024        /* top-k limit.  k <= 32 is the tuned case; above it the engine uses more DB  */
                               /* splits and sorts the per-query lists instead of extracting k items         */
@@ -35,6 +35,7 @@ extern "C" {
 #define B2K_E_NODEVICE (-4)   /* no CUDA device / wrong architecture            */
 #define B2K_E_NOMEM    (-5)   /* host allocation failure                        */
 #define B2K_E_UNSUPPORTED (-6) /* input format this fast path does not handle    */
+#define B2K_E_PEER     (-7)   /* a peer rank did not take part in the exchange  */
 
 typedef struct b2k_index b2k_index;
 
@@ -58,19 +59,21 @@ typedef struct b2k_index b2k_index;
 typedef struct b2k_stats {
   int32_t path;            /* last search: 1 = K-scan, 2 = K-score (1 CTA), 3 = K-score (CTA pairs) */
   int32_t n_splits;        /* DB splits (partial lists) per query                            */
-  int32_t n_rerank;        /* candidate slots per query                                      */
+  int32_t cand_slots;      /* candidate slots per query (capacity; rows actually re-ranked: n_candidates) */
   int32_t n_uncertified;   /* queries whose certificate failed -> served by exact fp32 scan  */
   float   eps_max;         /* largest certificate slack used (bound on |bf16 score - exact|) */
   float   err_max;         /* max_row ||bf16(x) - x||_2 over the shard                       */
   float   norm_max;        /* max_row ||x||_2 over the shard                                 */
   int32_t launches;        /* kernels launched by the last search                            */
-  float   score_ms;        /* device time of the scoring kernel(s) of the last pass (CUDA     */
-                           /* events on the launching stream; the roofline numerator's clock) */
-  float   tail_ms;         /* device time of select + rerank + finalize + exact of that pass  */
+  float   score_ms;        /* device time of the scoring kernel(s) (CUDA events on the         */
+                           /* launching stream; the roofline numerator's clock): mean over the */
+                           /* passes since the previous b2k_get_stats (the last 64 at most)    */
+  float   tail_ms;         /* same for select + rerank + finalize (+ collect / exact)          */
   int32_t n_queries;       /* queries of the last pass                                        */
   int32_t n_candidates;    /* rows re-ranked in fp32 over all queries of the last pass        */
   int32_t n_saturated;     /* (query, DB split) pairs whose partial list was full of candidates */
                            /* in the last pass: re-scanned by K-collect                        */
+  int32_t n_timed;         /* passes averaged into score_ms / tail_ms                          */
 } b2k_stats;
 
 typedef struct b2k_synth {
@@ -180,6 +183,11 @@ int  b2k_xchg_push(b2k_xchg* x, const float* ip, const float* dist, const int64_
                    int32_t k, void* stream);
 int  b2k_xchg_merge(b2k_xchg* x, int32_t nq, int32_t k, float* out_ip, float* out_dist,
                     int64_t* out_labels, void* stream);
+/* Synchronises the device and reports merges that gave up waiting for a peer (a dead or stalled rank: the
+ * merge kernel waits 10 s, pads its outputs with label -1 and returns instead of hanging or trapping, so the
+ * resident index survives).  *timed_out_ranks: bit g = rank g was missing; returns B2K_E_PEER when non-zero
+ * (the bits are cleared by the call). */
+int  b2k_xchg_status(b2k_xchg* x, uint32_t* timed_out_ranks);
 
 /* Replaces faiss.normalize_L2(x) (main/search_from_image.py:322): in place on a host
  * array, rows with zero norm untouched; computed on `device`. */
@@ -196,8 +204,11 @@ int b2k_save(b2k_index* idx, const char* path, const int64_t* ids, int64_t n_ids
  * on every rank alike. */
 int b2k_save_shard(b2k_index* idx, const char* path, const int64_t* ids, int64_t file_row_begin,
                    int64_t file_total_rows, int32_t create);
+/* capacity_rows: rows the loaded shard is allocated for (<= 0 or smaller than the range: exactly the
+ * range).  An index that is about to grow (--update) is loaded straight into its final capacity, so
+ * that no re-allocation (old + new arrays resident at once) ever happens. */
 int b2k_load(const char* path, int32_t device, int64_t row_begin, int64_t row_end,
-             b2k_index** out);
+             int64_t capacity_rows, b2k_index** out);
 int b2k_file_info(const char* path, int64_t* n_rows, int32_t* n_tables, int32_t* table_dims,
                   int32_t* has_ids);
 int b2k_load_ids(const char* path, int64_t row_begin, int64_t n, int64_t* ids_out);
@@ -208,7 +219,7 @@ int b2k_get_rows(b2k_index* idx, int64_t row0, int64_t n, float* f32_host,
 
 /* Device-side synthetic data for benches: appends n clustered rows whose
  * global offsets start at base_offset + ntotal; bit-reproducible on the CPU
- * (oracle/synth.py).  Queries are noisy copies of seeded DB rows, whole-vector normalised. */
+ * (oracle/b2k_oracle.c: orc_synth_rows).  Queries are noisy copies of seeded DB rows, whole-vector normalised. */
 int b2k_fill_synthetic(b2k_index* idx, int64_t n, const b2k_synth* p);
 int b2k_synth_queries_device(b2k_index* idx, int32_t nq, const b2k_synth* p, uint64_t qseed,
                              float sigma_q, float* q_dev, void* stream);

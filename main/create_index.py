@@ -146,7 +146,10 @@ class FAISSIndexBuilderDB:
 
     def _batch_records(self):
         select_cols, join_strs = self._make_select_and_joins()
-        query = f"SELECT {select_cols} FROM images i {join_strs}"
+        # the reference's join without an ORDER BY returns ascending images.id only because SQLite happens to
+        # drive it from `images`; offsets are defined by that order, so it is made explicit here
+        # (and is the order of the row-sharded build, whose files must equal a single-GPU build byte for byte)
+        query = f"SELECT {select_cols} FROM images i {join_strs} ORDER BY i.id"
         self.read_cur.execute(query)
         while True:
             rows = self.read_cur.fetchmany(self.batch_size)
@@ -233,7 +236,7 @@ class FAISSIndexBuilderDB:
         decoder below then rebuilds from scratch (pickle.loads semantics, row skipping included)."""
         from image_recommender_b200 import B2KError, _capi
         select_cols, join_strs = self._make_select_and_joins()
-        sql = f"SELECT {select_cols} FROM images i {join_strs}"
+        sql = f"SELECT {select_cols} FROM images i {join_strs} ORDER BY i.id"
         first = self.read_cur.execute(sql + " LIMIT 1").fetchone()
         if first is None:
             return None, []
@@ -285,7 +288,14 @@ class FAISSIndexBuilderDB:
         r0, r1 = shard_range(total, world, rank)
         select_cols, join_strs = self._make_select_and_joins()
         base_sql = f"SELECT {select_cols} FROM images i {join_strs}"
-        sql = f"{base_sql} ORDER BY i.id LIMIT {r1 - r0} OFFSET {r0}"
+        # keyset page instead of LIMIT/OFFSET (which re-scans the r0 joined rows before the page on every rank):
+        # the ids of the complete records, in order, give this rank's first and last id
+        all_ids = [r[0] for r in self.read_cur.execute(f"SELECT i.id FROM images i {join_strs} ORDER BY i.id")]
+        if r1 > r0:
+            sql = f"{base_sql} WHERE i.id BETWEEN {int(all_ids[r0])} AND {int(all_ids[r1 - 1])} ORDER BY i.id"
+        else:
+            sql = f"{base_sql} WHERE 0"
+        del all_ids
         first = self.read_cur.execute(base_sql + " ORDER BY i.id LIMIT 1").fetchone()
         dims = [int(self._decode_blob(b).shape[0]) for b in first[1:]]
         index = self._initialize_index(dims, max(r1 - r0, 1))
@@ -358,10 +368,17 @@ class FAISSIndexBuilderDB:
         if update_index and self.index_file.exists():
             from image_recommender_b200 import file_info, load_ids
             info = file_info(self.index_file)
-            index = FlatShard.load(self.index_file, device=self.device)
+            if not info["has_ids"] and info["n_rows"] > 0:
+                # without the id column (files written through faiss_shim.write_index) nothing tells which images
+                # the file already holds: every row would be added again.  Refuse before any work is done.
+                raise ValueError(f"{self.index_file} carries no image-id column: it cannot be updated in place; "
+                                 f"rebuild it (update_index=False)")
+            # straight into the final capacity: appending never re-allocates (a re-allocation holds the old and
+            # the new arrays at once, which a shard filling most of the GPU cannot afford)
+            index = FlatShard.load(self.index_file, device=self.device,
+                                   capacity=max(info["n_rows"], self._count_records()))
             offset_counter = index.ntotal
-            if info["has_ids"]:
-                all_ids = load_ids(self.index_file, 0, info["n_rows"]).tolist()
+            all_ids = load_ids(self.index_file, 0, info["n_rows"]).tolist() if info["has_ids"] else []
             known = set(all_ids)
             self._log(f"Appending to {self.index_file} ({offset_counter} vectors).", level="info")
         else:
