@@ -60,8 +60,11 @@ def apply_config(args):
         args.k = c["k"]
     if args.k is None:
         args.k = 10
-    if c.get("hnsw_rows") and args.hnsw_rows == 0:
-        args.hnsw_rows = c["hnsw_rows"]
+    if args.hnsw_rows < 0:
+        cores = len(os.sched_getaffinity(0))
+        args.hnsw_rows = min(c.get("hnsw_rows") or 50_000, 2500 * cores, c["rows"])
+    if args.cpu_batch <= 0:
+        args.cpu_batch = max(1, min(args.batch, 4096))
     args.workload_name = c["name"]
     args.scaling = "weak" if c["per_gpu"] and rows < c["rows"] else "strong"
     if args.config != "3":
@@ -73,7 +76,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-baseline-child"])
     ap.add_argument("--config", default="3", choices=sorted(CONFIGS), help="BASELINE.json config (default 3: the headline)")
     ap.add_argument("--rows", type=int, default=None, help="total database rows over all ranks (default: the config's)")
     ap.add_argument("--batch", type=int, default=None, help="queries per step (default: the config's; 4096 for config 3)")
@@ -83,26 +86,35 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: NVLink peer-memory exchange kernels (default) or NCCL all-gather + merge")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 force K-scan, 2 force K-score (debug)")
-    ap.add_argument("--hnsw-rows", type=int, default=0,
-                    help="> 0: also build the reference's HNSW (M=32, efC=200; oracle/hnsw_ref.c) on that many "
-                         "rows on the host and report recall@k / QPS for an efSearch sweep")
+    ap.add_argument("--hnsw-rows", type=int, default=-1,
+                    help="rows of the reference's HNSW (M=32, efC=200; oracle/hnsw_ref.c) built on the host for the "
+                         "recall@k / QPS column (efSearch sweep).  -1 (default): sized to the host so that the leg takes "
+                         "about 30 s (2500 rows per core, at most 50000); 0: off")
     ap.add_argument("--cpu-rows", type=int, default=400_000)
-    ap.add_argument("--cpu-batch", type=int, default=1024)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="queries of the CPU sample (default: the step's batch, <= 4096)")
+    ap.add_argument("--selfcheck", type=int, default=64,
+                    help="queries of the headline batch re-run with the exhaustive fp32 scan on every rank and compared "
+                         "bit for bit with the certified path's output (0: off)")
     args = ap.parse_args()
     apply_config(args)
     return args
 
 
+TRAFFIC_FILE = "profiles/r02_traffic.json"
+
+
 def load_traffic(kernel: str, rows_local: int, batch: int):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on exactly
-    this workload (profiles/r01_traffic.json); else None."""
-    p = ROOT / "profiles" / "r01_traffic.json"
-    if not p.exists():
-        return None
-    t = json.loads(p.read_text()).get(kernel)
-    if t and t["rows_local"] == rows_local and t["batch"] == batch:
-        return t["dram_bytes"]
-    return None
+    """(DRAM bytes per launch of `kernel`, source label) from the committed ncu capture, if it was taken on
+    exactly this workload; else (None, None).  The number is REPLAYED from the file, not measured in this run:
+    the label says so in the JSON line."""
+    for name in (TRAFFIC_FILE, "profiles/r01_traffic.json"):
+        p = ROOT / name
+        if not p.exists():
+            continue
+        t = json.loads(p.read_text()).get(kernel)
+        if t and t["rows_local"] == rows_local and t["batch"] == batch:
+            return t["dram_bytes"], f"{name} (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum; replayed, not measured in this run)"
+    return None, None
 
 
 def load_peaks():
@@ -162,46 +174,87 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_baseline(rows: int, batch: int, k: int, reps: int = 1):
-    """The oracle port of the reference's exact search (oracle/cpu_flat.py: sgemm blocks + top-k,
-    what faiss IndexFlatIP does) on a bounded sample, all host threads; QPS extrapolated
-    linearly in N to the 10 M-row workload."""
-    import numpy as np
-    import oracle
+def use_all_host_threads(n: int | None = None):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank: give the CPU arm back all the cores it may use
+    (OpenBLAS through threadpoolctl, the OpenMP heap loops through the port's own setter)."""
+    cores = n or len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores, user_api="blas")
+    except Exception:
+        pass
     from oracle import cpu_flat
-    cores = use_all_host_threads()
+    cpu_flat.set_num_threads(cores)
+    return cores
+
+
+def cpu_flat_sample(rows: int, batch: int):
+    """Synthetic sample for the CPU arms: (fp32 rows [rows, D] as K-pack stores them, queries [batch, D])."""
+    import oracle
     tabs = oracle.synth_rows(DIMS, rows, total_rows=rows)
     db = oracle.pack(tabs)["f32"]
     del tabs
-    q = oracle.synth_queries(DIMS, batch, rows)
-    cpu_flat.search_flat_ip(db[:4096], q[:32], k)        # warm BLAS threads
-    ts = []
-    for _ in range(reps):
+    return db, oracle.synth_queries(DIMS, batch, rows)
+
+
+def cpu_baseline(rows: int, batch: int, k: int, n_total: int):
+    """The oracle port of the reference's exact search (oracle/cpu_flat.py + cpu_flat.c: OpenBLAS sgemm blocks
+    + OpenMP per-query heaps, what faiss IndexFlatIP does) on a bounded sample, timed at a quarter, half and all
+    of the host threads (the port must scale with the cores, as faiss does); QPS extrapolated linearly in
+    the row count to the full workload.  Called in a child process by the GPU arm (CPU_BASELINE_CHILD): the
+    parent's CUDA context, pinned allocations and torch thread pools would otherwise share the cores."""
+    from oracle import cpu_flat
+    cores = len(os.sched_getaffinity(0))
+    db, q = cpu_flat_sample(rows, batch)
+    out = {}
+    for n in sorted({max(1, cores // 4), max(1, cores // 2), cores}):
+        use_all_host_threads(n)
+        cpu_flat.search_flat_ip(db[:8192], q[:64], k)        # warm the BLAS / OpenMP pools at this width
         t0 = time.perf_counter()
         cpu_flat.search_flat_ip(db, q, k)
-        ts.append(time.perf_counter() - t0)
-    t = min(ts)
-    return t, cores
+        out[n] = time.perf_counter() - t0
+    use_all_host_threads(cores)
+    t = out[cores]
+    return {"value": batch / t * (rows / n_total), "unit": UNIT, "cores": cores, "kind": "port",
+            "what": "exact-flat CPU port (faiss IndexFlatIP restated: OpenBLAS sgemm blocks 4096 x 1024 + OpenMP heaps), "
+                    "extrapolated in rows",
+            "sample": f"{batch} queries x {rows} rows x D={D} fp32 in {t:.2f} s on {cores} threads; QPS scaled linearly "
+                      f"to {n_total} rows (x{n_total / rows:.1f})",
+            "thread_scaling_qps": {str(n): batch / tt * (rows / n_total) for n, tt in out.items()}}
 
 
-def hnsw_baseline(rows: int, k: int, nq: int = 1000):
+def cpu_baseline_child(args, rows, n_total):
+    """Runs cpu_baseline() of this very configuration in a fresh interpreter and returns its dict."""
+    import subprocess
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "cpu-baseline-child", "--config", args.config,
+           "--rows", str(n_total), "--batch", str(args.batch), "--k", str(args.k), "--cpu-rows", str(rows),
+           "--cpu-batch", str(args.cpu_batch)]
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    if r.returncode != 0:
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def hnsw_baseline(rows: int, k: int, nq: int = 500):
     """recall@k and QPS of the reference's IndexHNSWFlat(M=32, efConstruction=200) restated on the
     host (oracle/hnsw_ref.c), against the exact ids of the same sample; efSearch sweep around the
-    reference's 64 / 50 (main/create_index.py:20-22, 336-339).  Queries are whole-vector-normalised,
-    rows have norm sqrt(3): the reference's own geometry."""
+    reference's 64 (main/create_index.py:20-22, 229-234).  Queries are whole-vector-normalised,
+    rows have norm sqrt(T): the reference's own geometry."""
     import numpy as np
-    import oracle
     from oracle import cpu_flat, hnsw_ref
-    db = oracle.pack(oracle.synth_rows(DIMS, rows, total_rows=rows))["f32"]
-    q = oracle.synth_queries(DIMS, nq, rows)
+    cores = use_all_host_threads()
+    db, q = cpu_flat_sample(rows, nq)
     _, exact = cpu_flat.search_flat_ip(db, q, k)
     ix = hnsw_ref.IndexHNSWFlat(D, 32, 200, 64)
     t0 = time.perf_counter()
     ix.add(db)
     build_s = time.perf_counter() - t0
-    out = {"rows": rows, "queries": nq, "M": 32, "efConstruction": 200, "build_s": build_s,
-           "cores": len(os.sched_getaffinity(0)), "kind": "port (oracle/hnsw_ref.c; faiss absent)", "efSearch": {}}
-    for ef in (16, 32, 50, 64, 128, 256):
+    out = {"rows": rows, "queries": nq, "M": 32, "efConstruction": 200, "build_s": build_s, "cores": cores,
+           "kind": "port (oracle/hnsw_ref.c; faiss absent)",
+           "note": "the reference's own index type on a host-sized subsample; its QPS does not extrapolate linearly in rows",
+           "efSearch": {}}
+    for ef in (16, 64, 256):
         ix.efSearch = ef
         ix.search(q[:32], k)
         t0 = time.perf_counter()
@@ -212,34 +265,21 @@ def hnsw_baseline(rows: int, k: int, nq: int = 1000):
     return out
 
 
-def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1 to every rank: give the CPU arm back all the cores it may use."""
-    cores = len(os.sched_getaffinity(0))
-    try:
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=cores)
-    except Exception:
-        pass
-    return cores
-
-
 def run_reference(args):
-    """--impl reference: the reference's own CPU path for this metric.  faiss_cpu is not
-    installable here, so this is the oracle port (kind 'port') on a bounded sample."""
+    """--impl reference: the reference's CPU path for this metric, on the box's host cores.  faiss_cpu is not
+    installable here, so this is the oracle port (kind 'port'): the EXACT-FLAT search the north star names as the
+    CPU yardstick (IndexFlatIP), each step one bounded sample of the workload (the step's batch against a slice of
+    the rows), `value` extrapolated linearly in rows and labelled so.  The reference's own index type (HNSW,
+    approximate) is timed beside it on a host-sized subsample with its recall."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     rows, batch = args.cpu_rows, args.cpu_batch
-    rows = max(1024, min(rows, int(rows * 1968 / D)))      # same host memory whatever the row width
-    import numpy as np
-    import oracle
+    rows = max(1024, min(rows, int(rows * 1968 / D), args.rows))      # same host memory whatever the row width
     from oracle import cpu_flat
     cores = use_all_host_threads()
-    tabs = oracle.synth_rows(DIMS, rows, total_rows=rows)
-    db = oracle.pack(tabs)["f32"]
-    del tabs
-    q = oracle.synth_queries(DIMS, batch, rows)
-    for _ in range(max(args.warmup, 1)):
+    db, q = cpu_flat_sample(rows, batch)
+    for _ in range(max(min(args.warmup, 2), 1)):
         cpu_flat.search_flat_ip(db[: max(rows // 8, 1024)], q, args.k)
     times = []
     for _ in range(args.steps):
@@ -248,25 +288,64 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
     qps = batch / t * (rows / args.rows)
-    sample = (f"{batch} queries x {rows} rows x D={D} fp32 per step (numpy/OpenBLAS sgemm blocks + top-k = faiss "
-              f"IndexFlatIP restated), QPS scaled linearly to {args.rows} rows")
+    what = "exact-flat CPU port (faiss IndexFlatIP restated: OpenBLAS sgemm + OpenMP heaps), extrapolated in rows"
+    sample = (f"{batch} queries x {rows} rows x D={D} fp32 per step, {cores} threads; QPS scaled linearly to "
+              f"{args.rows} rows (x{args.rows / rows:.1f})")
+    hnsw = None
+    if args.hnsw_rows > 0:
+        try:
+            hnsw = hnsw_baseline(args.hnsw_rows, args.k)
+        except Exception as e:
+            hnsw = {"error": str(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * (args.rows / rows) * (args.batch / batch),
+        "steps": args.steps, "warmup": args.warmup,
+        # the time of the step that was actually run (the bounded sample); the full-size figure is an extrapolation
+        "ms_per_step": t * 1e3,
+        "ms_per_step_extrapolated": t * 1e3 * (args.rows / rows) * (args.batch / batch),
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "same_config": False,
         "config": {"workload": f"{args.workload_name} D={D}, {args.rows} rows, batch {args.batch}, top-{args.k}",
-                   "sample": sample},
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                   "arm": what, "sample": sample},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "what": what, "sample": sample},
+        "hnsw_reference": hnsw,
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------
+def bits_equal(a, b):
+    """Bit-for-bit equality of two result triples (dist f32, labels i64, ip f32) of torch tensors."""
+    import torch
+    def raw(t):
+        return t.view(torch.int32) if t.dtype == torch.float32 else t
+    return bool(all(torch.equal(raw(x), raw(y)) for x, y in zip(a, b)))
+
+
+def host_merge(g_dist, g_lab, g_ip, k):
+    """Independent cross-shard merge on the host: every rank's list gathered, ONE global sort per query by
+    (ip descending, offset ascending), first k.  [G, nq, k] CPU tensors -> (dist, lab, ip) [nq, k]."""
+    import torch
+    G, nq, kk = g_lab.shape
+    lab = g_lab.permute(1, 0, 2).reshape(nq, G * kk)
+    ip = g_ip.permute(1, 0, 2).reshape(nq, G * kk)
+    dist = g_dist.permute(1, 0, 2).reshape(nq, G * kk)
+    big = torch.iinfo(torch.int64).max
+    o1 = torch.argsort(torch.where(lab < 0, torch.full_like(lab, big), lab), dim=1, stable=True)
+    ip1 = torch.gather(ip, 1, o1)
+    o2 = torch.argsort(-ip1.double(), dim=1, stable=True)      # stable: equal scores keep ascending offsets
+    order = torch.gather(o1, 1, o2)[:, :k]
+    return torch.gather(dist, 1, order), torch.gather(lab, 1, order), torch.gather(ip, 1, order)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "cpu-baseline-child":
+        print(json.dumps(cpu_baseline(args.cpu_rows, args.cpu_batch, args.k, args.rows)), flush=True)
         return
 
     import torch
@@ -292,7 +371,44 @@ def main():
     r0, r1 = shard_range(n_total, world, rank)
     n_local = r1 - r0
 
-    # ---- build the shard (K-pack timed as a side number)
+    # ---- K-pack (build half) timed alone, FIRST: the GPU is idle and cool, nothing else is resident.  Every
+    # launch is timed by its own pair of CUDA events; the median of >= 50 launches is reported with the SM
+    # clock sampled meanwhile (an HBM-bound kernel must not depend on it).
+    pack = None
+    if rank == 0:
+        n_pack, per_round, rounds = 131072, 8, 7
+        n_pack = max(1024, min(n_pack, int(n_pack * 1968 / D)))
+        scratch = irb.FlatShard(DIMS, n_pack * per_round, device=local_rank)
+        tabs = [torch.randn((n_pack, d), device=dev, dtype=torch.float32) for d in DIMS]
+        for _ in range(3):
+            scratch.add_tables_device(tabs)
+        torch.cuda.synchronize()
+        pack_sampler = ClockSampler(local_rank)
+        pack_sampler.start()
+        times = []
+        for _ in range(rounds):
+            scratch.reset()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(per_round)]
+            for e0, e1 in evs:
+                e0.record()
+                scratch.add_tables_device(tabs)
+                e1.record()
+            torch.cuda.synchronize()
+            times += [e0.elapsed_time(e1) for e0, e1 in evs]
+        pack_clocks = pack_sampler.stop()
+        ms_pack = statistics.median(times)
+        bytes_pack = n_pack * (4.0 * D + 4.0 * D + 2.0 * Dp + 4.0)       # read fp32, write fp32 + bf16 + norm
+        pack = {"bound": "hbm", "kernel": "pack_rows_kernel", "rows_per_launch": n_pack, "kernel_ms": ms_pack,
+                "launches_timed": len(times), "kernel_ms_min": min(times), "kernel_ms_max": max(times),
+                "achieved": bytes_pack / (ms_pack * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": bytes_pack / (ms_pack * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "rows_per_s": n_pack / (ms_pack * 1e-3), "sm_mhz": pack_clocks["sm_mhz"],
+                "algorithmic_bytes_per_launch": bytes_pack}
+        scratch.close()
+        del tabs, scratch
+        torch.cuda.empty_cache()
+
+    # ---- build the shard
     shard = irb.FlatShard(DIMS, n_local, device=local_rank, base_offset=r0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -315,39 +431,29 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def time_device(qd, steps, warmup):
-        """K steps with inputs resident in HBM; CUDA events on the launching stream; max over ranks."""
+    def time_device(qd, steps, warmup, srch=None):
+        """K steps with inputs resident in HBM; CUDA events on the launching stream; max over ranks.
+        Returns (ms per step, stats): stats.score_ms / tail_ms are the scoring / tail kernel times of THESE
+        steps (event triples recorded inside the C ABI around the launches, averaged over the last <= 64
+        steps; no host sync between the steps), so kernel_ms <= ms_per_step by construction."""
+        srch = srch or searcher
         for _ in range(warmup):
-            searcher.search_device(qd, k)
+            srch.search_device(qd, k)
         barrier()
+        shard.stats()                  # forget the warm-up passes
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            searcher.search_device(qd, k)
+            srch.search_device(qd, k)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        st = shard.stats()
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / steps
-
-    def kernel_times(qd, steps):
-        """Average device time of the scoring kernel (CUDA events inside the C ABI, on the
-        launching stream) and of the tail kernels, over `steps` steady-state steps."""
-        sc, tl, launches, unc = [], [], 0, 0
-        # stats() synchronises: small batches are preceded by two untimed back-to-back searches so that the
-        # timed kernel runs in the steady state of the timed region, not right after an idle gap
-        lead = 2 if qd.shape[0] <= 1024 else 0
-        for _ in range(steps):
-            for _ in range(lead):
-                searcher.search_device(qd, k)
-            searcher.search_device(qd, k)
-            st = shard.stats()
-            sc.append(st["score_ms"]); tl.append(st["tail_ms"]); launches = st["launches"]
-            unc += max(st["n_uncertified"], 0)
-        return sum(sc) / len(sc), sum(tl) / len(tl), launches, unc, st
+        return ms / steps, st
 
     def time_e2e(q_host, steps, warmup):
         """Through the public host-buffer API: pinned host queries -> H2D -> search (-> all-gather
@@ -358,7 +464,6 @@ def main():
         def step():
             if world == 1:
                 # the C-ABI host entry point (b2k_search): copies inside, synchronous
-                import ctypes as C
                 _capi.check(_capi.load_library().b2k_search(
                     shard._h, q_host.data_ptr(), q_host.shape[0], k, out_d.data_ptr(), out_l.data_ptr(), None))
             else:
@@ -381,82 +486,98 @@ def main():
             dt = float(t.item())
         return dt, q_host.numel() * 4, out_d.numel() * 4 + out_l.numel() * 8
 
+    KNAME = {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}
+
     # ---- headline: batch B
     qd = shard.synth_queries_device(B, total_rows=n_total)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_step = time_device(qd, args.steps, args.warmup)
+    ms_step, st = time_device(qd, args.steps, args.warmup)
     clocks = sampler.stop()
-    score_ms, tail_ms, launches, n_unc, st = kernel_times(qd, max(3, min(args.steps, 10)))
+    score_ms, tail_ms, launches = st["score_ms"], st["tail_ms"], st["launches"]
+    n_unc = max(st["n_uncertified"], 0)
+    certified = [t.clone() for t in searcher.search_device(qd, k)]     # the headline path's own output
+    torch.cuda.synchronize()
     q_host = qd.cpu().pin_memory()
     e2e_s, h2d, d2h = time_e2e(q_host, args.steps, args.warmup)
 
     flops = 2.0 * B * n_local * D
     tc_ach = flops / (score_ms * 1e-3) / 1e12
-    kname = {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st["path"]]
+    kname = KNAME[st["path"]]
+    traffic, traffic_src = load_traffic(kname, n_local, B)
     roofline = {"bound": "tensor", "achieved": tc_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": tc_ach / peaks["bf16_tflops"], "traffic": load_traffic(kname, n_local, B),
-                "kernel": kname,
-                "kernel_ms": score_ms, "peak_source": peaks["source"] + " burst (kernel timed alone per step)",
-                # the kernel IS the long step (122 of 127 ms): the sustained library figure is its fair ceiling;
+                "frac": tc_ach / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": kname, "kernel_ms": score_ms, "launches_averaged": st["n_timed"],
+                "peak_source": peaks["source"] + " burst (8192^3 cuBLAS GEMM)",
+                # the kernel IS the long step: the sustained library figure is its fair ceiling;
                 # `frac` stays against the burst peak (conservative)
                 "peak_sustained": peaks["bf16_tflops_sustained"], "frac_vs_sustained": tc_ach / peaks["bf16_tflops_sustained"],
                 "algorithmic_flops_per_launch": flops}
     if B <= 128:     # small headline batch (configs 4, 5): the scoring kernel is HBM-bound
         ach = 2.0 * n_local * D / (score_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": load_traffic(kname, n_local, B), "kernel": kname,
-                    "kernel_ms": score_ms, "peak_source": peaks["source"] + " copy bandwidth",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "kernel": kname,
+                    "kernel_ms": score_ms, "launches_averaged": st["n_timed"],
+                    "peak_source": peaks["source"] + " copy bandwidth",
                     "algorithmic_bytes_per_launch": 2.0 * n_local * D}
 
     # ---- batch-1 (HBM-bound) leg, reported alongside
     q1 = qd[:1].contiguous()
-    ms_b1 = time_device(q1, max(args.steps, 20), max(args.warmup, 5))
-    s1_ms, t1_ms, l1, _, st1 = kernel_times(q1, 10)
+    ms_b1, st1 = time_device(q1, max(args.steps, 20), max(args.warmup, 5))
+    s1_ms, t1_ms = st1["score_ms"], st1["tail_ms"]
     bytes_b1 = 2.0 * n_local * D
     hbm_ach = bytes_b1 / (s1_ms * 1e-3) / 1e9
-    kname1 = {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}[st1["path"]]
+    kname1 = KNAME[st1["path"]]
+    traffic1, traffic1_src = load_traffic(kname1, n_local, 1)
     roofline_b1 = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": hbm_ach / peaks["hbm_gbs"], "traffic": load_traffic(kname1, n_local, 1),
-                   "kernel": kname1,
-                   "kernel_ms": s1_ms,
-                   "qps": 1e3 / ms_b1, "ms_per_query": ms_b1, "tail_ms": t1_ms,
+                   "frac": hbm_ach / peaks["hbm_gbs"], "traffic": traffic1, "traffic_source": traffic1_src,
+                   "kernel": kname1, "kernel_ms": s1_ms, "launches_averaged": st1["n_timed"],
+                   "qps": 1e3 / ms_b1, "ms_per_query": ms_b1, "tail_ms": t1_ms, "launches_per_query": st1["launches"],
                    "algorithmic_bytes_per_launch": bytes_b1}
 
-    # ---- K-pack (build half) timed alone on device-resident per-table rows
-    pack = None
-    if rank == 0:
-        n_pack, reps = 131072, 6
-        n_pack = max(1024, min(n_pack, int(n_pack * 1968 / D)))
-        scratch = irb.FlatShard(DIMS, n_pack * (reps + 2), device=local_rank)
-        tabs = [torch.randn((n_pack, d), device=dev, dtype=torch.float32) for d in DIMS]
-        for _ in range(2):
-            scratch.add_tables_device(tabs)
+    # ---- exactness self-check at bench scale, on every rank (the certificate is not taken on trust): a slice of
+    # the headline batch is searched again with the exhaustive fp32 scan forced on every rank's shard, merged
+    # through the same exchange, and must equal the certified path's output bit for bit; at N > 1 the exchanged
+    # result must also equal an independent host-side merge of the all-gathered per-shard lists.
+    selfcheck = None
+    if args.selfcheck > 0:
+        nsc = min(args.selfcheck, B)
+        idx = torch.linspace(0, B - 1, nsc, device=dev).round().long()
+        qs = qd[idx].contiguous()
+        shard.set_option(_capi.OPT_FORCE_EXACT, 1)
+        exact = [t.clone() for t in searcher.search_device(qs, k)]
+        local = [t.clone() for t in shard.search_device(qs, k)]          # this rank's exhaustive local top-k
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            scratch.add_tables_device(tabs)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_pack = e0.elapsed_time(e1) / reps
-        bytes_pack = n_pack * (4.0 * D + 4.0 * D + 2.0 * Dp + 4.0)       # read fp32, write fp32 + bf16 + norm
-        pack = {"bound": "hbm", "kernel": "pack_rows_kernel", "rows_per_launch": n_pack, "kernel_ms": ms_pack,
-                "achieved": bytes_pack / (ms_pack * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": bytes_pack / (ms_pack * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                "rows_per_s": n_pack / (ms_pack * 1e-3)}
-        scratch.close()
-        del tabs
+        forced = shard.stats()["n_uncertified"]
+        shard.set_option(_capi.OPT_FORCE_EXACT, 0)
+        ok_exact = bits_equal(exact, [t[idx] for t in certified]) and forced == nsc
+        ok_merge = None
+        if world > 1:
+            gathered = []
+            for t in local:
+                g = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+                dist.all_gather_into_tensor(g, t.contiguous())
+                gathered.append(g.cpu())
+            ref = host_merge(gathered[0], gathered[1], gathered[2], k)
+            ok_merge = bits_equal([t.cpu() for t in exact], ref)
+        ok = torch.tensor([1 if (ok_exact and ok_merge is not False) else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        selfcheck = {"queries": nsc, "equal": bool(ok.item()), "ranks": world,
+                     "what": "FORCE_EXACT (exhaustive fp32 scan) on every rank's shard vs the certified headline output: "
+                             "labels, ip and dist bit for bit" + ("; exchange result == host merge of the all-gathered lists" if world > 1 else ""),
+                     "forced_exact_queries": forced, "host_merge_equal": ok_merge}
 
     sweep = {}
     for b in [int(x) for x in args.sweep.split(",") if x]:
         qb = shard.synth_queries_device(b, total_rows=n_total, qseed=0x5EED + b)
-        ms = time_device(qb, max(3, args.steps // 2), 3)
-        sm, tm, _, un, sst = kernel_times(qb, 3)
-        sweep[str(b)] = {"qps": b / ms * 1e3, "ms": ms, "score_ms": sm, "tail_ms": tm, "path": sst["path"],
+        ms, sst = time_device(qb, max(10, args.steps), 3)
+        sm = sst["score_ms"]
+        sweep[str(b)] = {"qps": b / ms * 1e3, "ms": ms, "score_ms": sm, "tail_ms": sst["tail_ms"], "path": sst["path"],
+                         "launches": sst["launches"],
                          "hbm_frac": 2.0 * n_local * D / (sm * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "tc_frac": 2.0 * b * n_local * D / (sm * 1e-3) / 1e12 / peaks["bf16_tflops"],
-                         "uncertified": un}
+                         "uncertified": max(sst["n_uncertified"], 0)}
 
     # ---- N > 1: the peer-memory exchange and the NCCL all-gather path must agree bit for bit
     exchange_check = None
@@ -467,14 +588,9 @@ def main():
         a = [t.clone() for t in searcher.search_device(qc, k)]
         b = [t.clone() for t in alt.search_device(qc, k)]
         torch.cuda.synchronize()
-        exchange_check = bool(all(torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
-                                              y.view(torch.int32) if y.dtype == torch.float32 else y)
-                                  for x, y in zip(a, b)))
+        exchange_check = bits_equal(a, b)
         # and the alternative path's timing for the record (batch 1 and headline batch)
-        searcher_main = searcher
-        searcher = alt
-        alt_ms = {"1": time_device(q1, max(args.steps, 20), 5), str(B): time_device(qd, args.steps, args.warmup)}
-        searcher = searcher_main
+        alt_ms = {"1": time_device(q1, max(args.steps, 20), 5, alt)[0], str(B): time_device(qd, args.steps, args.warmup, alt)[0]}
     else:
         alt_ms = None
 
@@ -511,16 +627,15 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_rows = max(1024, min(args.cpu_rows, int(args.cpu_rows * 1968 / D)))
-        t_cpu, cores = cpu_baseline(cpu_rows, args.cpu_batch, k)
-        qps_cpu = args.cpu_batch / t_cpu * (cpu_rows / n_total)
-        cpu = {"value": qps_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_batch} queries x {cpu_rows} rows x D={D} fp32 in {t_cpu:.2f} s (numpy/OpenBLAS "
-                         f"sgemm blocks + top-k = faiss IndexFlatIP restated); QPS scaled linearly to {n_total} rows"}
+        cpu_rows = max(1024, min(args.cpu_rows, int(args.cpu_rows * 1968 / D), n_total))
+        cpu = cpu_baseline_child(args, cpu_rows, n_total)
 
     hnsw = None
-    if rank == 0 and world == 1 and args.hnsw_rows > 0:
-        hnsw = hnsw_baseline(args.hnsw_rows, k)
+    if rank == 0 and world == 1 and args.hnsw_rows > 0 and not args.no_cpu_baseline:
+        try:
+            hnsw = hnsw_baseline(args.hnsw_rows, k)
+        except Exception as e:      # a reported baseline must never fail the bench
+            hnsw = {"error": str(e)[:200]}
 
     if rank == 0:
         line = {
@@ -537,6 +652,7 @@ def main():
             "gpu_launches": args.steps * (launches + ((2 if exchange is not None else 1) if world > 1 else 0)),
             "clocks": clocks,
             "extra": {"score_ms": score_ms, "tail_ms": tail_ms, "uncertified_queries": n_unc,
+                      "selfcheck": selfcheck,
                       "launches_per_step": launches, "exchange": (args.exchange if world > 1 else None), "exchange_matches_nccl": exchange_check,
                       "nccl_path_ms": alt_ms, "build_rows_per_s": n_local / build_s,
                       "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * Dp) / build_s / 1e9,
@@ -547,6 +663,8 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if selfcheck is not None and not selfcheck["equal"]:
+        sys.exit(3)          # a result that differs from exhaustive fp32 search is not a benchmark result
 
 
 if __name__ == "__main__":

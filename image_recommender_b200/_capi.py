@@ -70,6 +70,10 @@ SIGNATURES = {
                              C.c_void_p]),
     "b2k_search_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2k_search_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2k_prep_groups_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.c_void_p]),
     "b2k_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "b2k_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     "b2k_merge_topk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

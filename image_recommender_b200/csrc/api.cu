@@ -57,6 +57,9 @@ struct Workspace {
   int nq_cap = 0, n_lists = 0, cand_cap = 0, exact_splits = 0, k_cap = 0;
   unsigned long long* exact_ceil = nullptr;   // [nq] K-exact paging: key of the last emitted result per failed slot
   float* q = nullptr;             // [nq, D] staging for the host API
+  float* parts = nullptr;         // [parts_cap, D] image vectors of b2k_search_groups
+  int32_t* goffs = nullptr;       // [nq + 1] group offsets
+  int64_t parts_cap = 0;
   uint16_t* q_bf16 = nullptr;     // [nq_pad, Dp]
   float *qn2 = nullptr, *eps_scan = nullptr, *eps_tc = nullptr, *thr = nullptr, *thr_floor = nullptr, *lb = nullptr;
   int2* sat_pairs = nullptr;      // [sat_cap] saturated (query, list) pairs of the last pass (K-collect's work list)
@@ -69,7 +72,7 @@ struct Workspace {
   float *out_ip = nullptr, *out_dist = nullptr;
   int64_t* out_labels = nullptr;
   void release() {
-    dev_free(q); dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr); dev_free(thr_floor);
+    dev_free(q); dev_free(parts); dev_free(goffs); parts_cap = 0; dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr); dev_free(thr_floor);
     dev_free(lb); dev_free(sat_pairs); dev_free(exact_ceil);
     dev_free(partial); dev_free(cand_rows); dev_free(cand_count); dev_free(flags); dev_free(cand_ip);
     dev_free(fail_count); dev_free(fail_list); dev_free(exact_partial);
@@ -172,6 +175,7 @@ int ensure_workspace(b2k_index* ix, int nq, int k) {
   const int nq_pad = (cap + 255) / 256 * 256;
   int rc = 0;
   if ((rc = dev_alloc(&w.q, (size_t)cap * ix->D))) return rc;
+  if ((rc = dev_alloc(&w.goffs, (size_t)cap + 1))) return rc;
   if ((rc = dev_alloc(&w.q_bf16, (size_t)nq_pad * ix->Dp))) return rc;
   if ((rc = dev_alloc(&w.qn2, cap))) return rc;
   if ((rc = dev_alloc(&w.eps_scan, cap))) return rc;
@@ -692,6 +696,62 @@ int b2k_search(b2k_index* ix, const float* q_host, int32_t nq, int32_t k, float*
     if (ip_host)
       B2K_CUDA(cudaMemcpyAsync(ip_host + (int64_t)q0 * k, w.out_ip, (size_t)m * k * sizeof(float),
                                cudaMemcpyDeviceToHost, st));
+    B2K_CUDA(cudaMemcpyAsync(ix->h_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2K_CUDA(cudaStreamSynchronize(st));
+    n_fail += ix->h_fail[0];
+  }
+  ix->stats.n_uncertified = n_fail;
+  return 0;
+}
+
+int b2k_prep_groups_device(const float* parts_dev, const int32_t* group_offsets_dev, int32_t n_groups, int32_t d,
+                           float* q_dev, int32_t device, void* stream) {
+  if (!parts_dev || !group_offsets_dev || !q_dev || n_groups < 0 || d < 1) { set_error("prep_groups: bad argument"); return B2K_E_INVALID; }
+  DeviceGuard g(device);
+  return launch_group_prep(parts_dev, group_offsets_dev, n_groups, d, q_dev, (cudaStream_t)stream);
+}
+
+int b2k_search_groups(b2k_index* ix, const float* parts_host, int64_t n_images, const int32_t* group_offsets,
+                      int32_t n_groups, int32_t k, float* dist_host, int64_t* labels_host, float* ip_host) {
+  int rc = check_search_args(ix, parts_host, n_groups, k, dist_host, labels_host);
+  if (rc) return rc;
+  if (!group_offsets || n_images < n_groups || group_offsets[0] != 0 || group_offsets[n_groups] != n_images) {
+    set_error("search_groups: offsets must run from 0 to n_images (%lld) with no empty group", (long long)n_images);
+    return B2K_E_INVALID;
+  }
+  for (int g = 0; g < n_groups; ++g)
+    if (group_offsets[g + 1] <= group_offsets[g]) { set_error("search_groups: group %d is empty", g); return B2K_E_INVALID; }
+  DeviceGuard g(ix->device);
+  Workspace& w = ix->ws;
+  cudaStream_t st = ix->stream;
+  int n_fail = 0;
+  for (int g0 = 0; g0 < n_groups; g0 += kMaxNqPerPass) {
+    const int m = std::min(kMaxNqPerPass, n_groups - g0);
+    rc = ensure_workspace(ix, m, k);
+    if (rc) return rc;
+    const int64_t r0 = group_offsets[g0], r1 = group_offsets[g0 + m];
+    if (r1 - r0 > w.parts_cap) {
+      B2K_CUDA(cudaStreamSynchronize(st));
+      dev_free(w.parts);
+      w.parts_cap = 0;
+      if ((rc = dev_alloc(&w.parts, (size_t)(r1 - r0) * ix->D))) return rc;
+      w.parts_cap = r1 - r0;
+    }
+    // offsets of this pass, rebased to its first image (the host array is borrowed: staged synchronously)
+    std::vector<int32_t> offs((size_t)m + 1);
+    for (int i = 0; i <= m; ++i) offs[i] = (int32_t)(group_offsets[g0 + i] - r0);
+    B2K_CUDA(cudaMemcpyAsync(w.parts, parts_host + r0 * ix->D, (size_t)(r1 - r0) * ix->D * sizeof(float), cudaMemcpyHostToDevice, st));
+    B2K_CUDA(cudaMemcpyAsync(w.goffs, offs.data(), offs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    B2K_CUDA(cudaStreamSynchronize(st));                 // offs goes out of scope; pageable copies are staged anyway
+    // mean over the group's images + whole-vector normalise, straight into the search workspace
+    rc = launch_group_prep(w.parts, w.goffs, m, ix->D, w.q, st);
+    if (rc) return rc;
+    rc = search_pass(ix, w.q, m, k, w.out_dist, w.out_labels, w.out_ip, st);
+    if (rc) return rc;
+    B2K_CUDA(cudaMemcpyAsync(dist_host + (int64_t)g0 * k, w.out_dist, (size_t)m * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2K_CUDA(cudaMemcpyAsync(labels_host + (int64_t)g0 * k, w.out_labels, (size_t)m * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (ip_host)
+      B2K_CUDA(cudaMemcpyAsync(ip_host + (int64_t)g0 * k, w.out_ip, (size_t)m * k * sizeof(float), cudaMemcpyDeviceToHost, st));
     B2K_CUDA(cudaMemcpyAsync(ix->h_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     B2K_CUDA(cudaStreamSynchronize(st));
     n_fail += ix->h_fail[0];

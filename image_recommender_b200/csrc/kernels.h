@@ -153,6 +153,8 @@ struct MergeArgs {
 int launch_pack(const PackArgs& a, cudaStream_t st);
 int launch_normalize(float* x, int64_t n, int d, cudaStream_t st);
 int launch_query_prep(const QueryPrepArgs& a, cudaStream_t st);
+// groups of image vectors -> mean -> whole-vector L2 normalise (main/search_from_image.py:305-322)
+int launch_group_prep(const float* parts, const int32_t* offs, int n_groups, int d, float* q_out, cudaStream_t st);
 int launch_synth(const SynthArgs& a, cudaStream_t st);
 
 // K-scan: returns the number of splits it will use for a device with n_sm SMs.

@@ -166,6 +166,23 @@ class FlatShard:
                                   ip.ctypes.data if want_ip else None))
         return dist, lab, ip
 
+    def search_groups(self, parts, group_offsets, k: int, want_ip: bool = False):
+        """One query per GROUP of image vectors (search_from_image.py:305-322 + :247): parts [n_images, D] float32,
+        group g = rows [group_offsets[g], group_offsets[g+1]).  Mean, whole-vector normalisation and search all
+        happen on the device (b2k_search_groups); returns (distances, labels[, ip]) with one row per group."""
+        parts = _as_f32_2d(parts, "search_groups")
+        offs = np.ascontiguousarray(group_offsets, dtype=np.int32)
+        if parts.shape[1] != self.d:
+            raise ValueError(f"search_groups: vectors have {parts.shape[1]} columns, index dimension is {self.d}")
+        ng = offs.size - 1
+        dist = np.empty((ng, k), np.float32)
+        lab = np.empty((ng, k), np.int64)
+        ip = np.empty((ng, k), np.float32) if want_ip else None
+        if ng > 0:
+            check(_lib.b2k_search_groups(self._h, parts.ctypes.data, parts.shape[0], offs.ctypes.data, ng, int(k),
+                                         dist.ctypes.data, lab.ctypes.data, ip.ctypes.data if want_ip else None))
+        return (dist, lab, ip) if want_ip else (dist, lab)
+
     # ---- device-resident (torch) variants -------------------------------------------------
     def search_device(self, q, k: int, out=None, stream=None):
         """q: CUDA float32 [nq, D] torch tensor on this shard's device.  Enqueues on the current

@@ -204,6 +204,38 @@ class ShardedIndex:
             self.exchange.check()       # a rank that never published -> B2KError instead of -1 labels
         return dist_out, lab_out
 
+    def search_groups(self, parts, group_offsets, k: int):
+        """FlatShard.search_groups over the row-sharded index: every rank copies the (identical) image vectors to
+        its GPU, runs the mean + normalise kernel there and searches its shard; one exchange as in `search`."""
+        import ctypes as C
+        import numpy as np
+        import torch
+        from . import _capi
+        parts = np.ascontiguousarray(parts, dtype=np.float32)
+        offs = np.ascontiguousarray(group_offsets, dtype=np.int32)
+        ng = offs.size - 1
+        dev = torch.device("cuda", self.shard.device)
+        dist_out = np.empty((ng, k), np.float32)
+        lab_out = np.empty((ng, k), np.int64)
+        step = getattr(self, "_max_batch", 4096)
+        lib = _capi.load_library()
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for lo in range(0, ng, step):
+                hi = min(ng, lo + step)
+                r0, r1 = int(offs[lo]), int(offs[hi])
+                pd = torch.from_numpy(parts[r0:r1]).to(dev)
+                od = torch.from_numpy(offs[lo:hi + 1] - r0).to(dev)
+                qd = torch.empty((hi - lo, self.d), dtype=torch.float32, device=dev)
+                _capi.check(lib.b2k_prep_groups_device(pd.data_ptr(), od.data_ptr(), hi - lo, self.d, qd.data_ptr(),
+                                                       self.shard.device, C.c_void_p(st)))
+                d_, l_, _ = self._searcher.search_device(qd, k)
+                dist_out[lo:hi] = d_.cpu().numpy()
+                lab_out[lo:hi] = l_.cpu().numpy()
+        if self.exchange is not None:
+            self.exchange.check()
+        return dist_out, lab_out
+
     def close(self) -> None:
         if self.exchange is not None:
             self.exchange.close()

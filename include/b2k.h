@@ -155,6 +155,19 @@ int b2k_search(b2k_index* idx, const float* q_host, int32_t nq, int32_t k,
  * The index owns one search workspace: use one stream at a time per index. */
 int b2k_search_device(b2k_index* idx, const float* q_dev, int32_t nq, int32_t k,
                       float* dist_dev, int64_t* labels_dev, float* ip_dev, void* stream);
+/* Replaces the query-vector assembly of ImageRecommender._extract_query_vector together with the search
+ * (main/search_from_image.py:305-322 + :247) for MANY query groups at once: parts_host is the [n_images, D]
+ * matrix of concatenated per-image vectors (row = np.concatenate(parts, axis=1), :309), group g owns rows
+ * [group_offsets[g], group_offsets[g+1]) (offsets[0] = 0, offsets[n_groups] = n_images, no empty group).  On
+ * the device: np.mean over the group's images (:317; fp32, images added in order, one division), then
+ * faiss.normalize_L2 of the mean (:322), written straight into the search workspace — the normalised
+ * queries never travel back to the host — then the search.  Outputs as b2k_search, one row per group. */
+int b2k_search_groups(b2k_index* idx, const float* parts_host, int64_t n_images, const int32_t* group_offsets,
+                      int32_t n_groups, int32_t k, float* dist_host, int64_t* labels_host, float* ip_host);
+/* The prep step alone on device buffers (row-sharded deployments run it on every rank before the local
+ * search): q_dev [n_groups, d] = normalize_L2(mean of each group's rows). */
+int b2k_prep_groups_device(const float* parts_dev, const int32_t* group_offsets_dev, int32_t n_groups, int32_t d,
+                           float* q_dev, int32_t device, void* stream);
 int b2k_get_stats(b2k_index* idx, b2k_stats* out);   /* synchronises the last search */
 int b2k_set_option(b2k_index* idx, int32_t key, int64_t value);
 

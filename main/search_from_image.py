@@ -144,10 +144,12 @@ class ImageRecommender:
         # same arithmetic as _extract_query_vector / _fetch_results (kept below in the reference's shape and
         # checked equal), through IN-selects on one persistent connection and the resident id column:
         # 0.8 ms -> 0.3 ms of host time per query, next to 0.9 ms of GPU time on eight GPUs
-        query_vec, live = self._extract_query_matrix([paths_rel], file_order)
-        if query_vec is None:
+        parts, offs, live = self._extract_query_parts([paths_rel], file_order)
+        if parts is None:
             return None
-        distances, indices = index.search(query_vec, self.top_k)
+        # mean over the query images, faiss.normalize_L2 and the search run on the device in one call
+        # (b2k_search_groups): the normalised vector never travels back to the host
+        distances, indices = index.search_groups(parts, offs, self.top_k)
         results = self._fetch_results_batch(indices, distances, offset_table, index)[0]
         if not results:
             logging.error("No similar images found.")
@@ -171,11 +173,11 @@ class ImageRecommender:
         if index is None:
             return None
         groups_rel = [[self._relative(p) for p in g] for g in query_groups]
-        q, live = self._extract_query_matrix(groups_rel, file_order)
+        parts, offs, live = self._extract_query_parts(groups_rel, file_order)
         out = [None] * len(groups_rel)
-        if q is None:
+        if parts is None:
             return out
-        distances, indices = index.search(q, self.top_k)
+        distances, indices = index.search_groups(parts, offs, self.top_k)
         for row, res in zip(live, self._fetch_results_batch(indices, distances, offset_table, index)):
             out[row] = res or None
         return out
@@ -230,6 +232,28 @@ class ImageRecommender:
                 continue
             out[p] = np.concatenate(parts, axis=1).astype("float32")
         return out
+
+    def _extract_query_parts(self, groups_rel, ordered):
+        """([n_images, D] concatenated per-image vectors, int32 group offsets [G'+1], indices of the groups
+        kept) — the inputs of `search_groups`, which takes the mean of every group, normalises it and searches
+        on the device.  Groups without any usable image are dropped (logged), as _extract_query_vector does."""
+        if any(t not in TABLES for t in ordered):
+            logging.error(f"Unknown vector type in {ordered}.")
+            return None, None, []
+        vecs = self._fetch_vectors_batch([p for g in groups_rel for p in g], ordered)
+        rows, offs, live = [], [0], []
+        for gi, g in enumerate(groups_rel):
+            have = [vecs[p] for p in g if p in vecs]
+            if not have:
+                logging.error("Could not extract a vector for any of the query images.")
+                continue
+            rows.extend(have)
+            offs.append(offs[-1] + len(have))
+            live.append(gi)
+        if not live:
+            return None, None, []
+        parts = np.ascontiguousarray(np.concatenate(rows, axis=0), dtype=np.float32)
+        return parts, np.asarray(offs, dtype=np.int32), live
 
     def _extract_query_matrix(self, groups_rel, ordered):
         """([G', D] normalised query matrix, indices of the groups it holds) — row g is bit-identical
