@@ -16,6 +16,7 @@ B2K_MAX_K = 1024
 B2K_LIST = 32
 
 OPT_PATH, OPT_RERANK, OPT_FORCE_EXACT, OPT_SCAN_MAX_B, OPT_SPLITS, OPT_TC_PAIR, OPT_SEED, OPT_TIGHTEN, OPT_COLLECT, OPT_INLINE_SEED = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+OPT_FUSED_TAIL = 11
 PATH_AUTO, PATH_SCAN, PATH_TC = 0, 1, 2
 E_INVALID, E_CAPACITY, E_IO, E_NODEVICE, E_NOMEM, E_UNSUPPORTED, E_PEER = -1, -2, -3, -4, -5, -6, -7
 
@@ -86,6 +87,21 @@ SIGNATURES = {
     "b2k_xchg_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b2k_xchg_merge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2k_xchg_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "b2k_group_create": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
+    "b2k_group_destroy": (None, [C.c_void_p]),
+    "b2k_group_size": (C.c_int32, [C.c_void_p]),
+    "b2k_group_load": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "b2k_group_set_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "b2k_group_shard": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "b2k_group_ntotal": (C.c_int64, [C.c_void_p]),
+    "b2k_group_dim": (C.c_int32, [C.c_void_p]),
+    "b2k_group_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2k_group_put_queries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "b2k_group_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "b2k_group_get_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2k_group_search_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2k_group_last_run_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "b2k_normalize_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "b2k_save": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "b2k_save_shard": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),

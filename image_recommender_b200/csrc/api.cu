@@ -31,6 +31,7 @@ namespace {
 constexpr int64_t kMaxStageRows = 65536;  // rows per staging chunk of add() / load() / fill_synthetic() (fewer for very wide rows)
 constexpr int kMaxNqPerPass = 16384;      // queries per pipeline pass (workspace sizing)
 constexpr int kDefaultCandCap = 0;      // 0: every listed entry can be a candidate (no overflow)
+constexpr int kCounterHead = 4;          // ints in front of the per-query counters of Workspace::fail_count
 constexpr int kEvRing = 64;             // pipeline passes whose device times b2k_get_stats can average
 
 struct DeviceGuard {
@@ -67,7 +68,7 @@ struct Workspace {
   Cand* partial = nullptr;        // [nq, n_lists, 32]
   int32_t *cand_rows = nullptr, *cand_count = nullptr, *flags = nullptr;
   float* cand_ip = nullptr;
-  int32_t *fail_count = nullptr, *fail_list = nullptr;
+  int32_t *fail_count = nullptr, *fail_list = nullptr, *state = nullptr, *sat_n = nullptr;
   Cand* exact_partial = nullptr;  // [nq, exact_splits, 32]
   float *out_ip = nullptr, *out_dist = nullptr;
   int64_t* out_labels = nullptr;
@@ -75,7 +76,7 @@ struct Workspace {
     dev_free(q); dev_free(parts); dev_free(goffs); parts_cap = 0; dev_free(q_bf16); dev_free(qn2); dev_free(eps_scan); dev_free(eps_tc); dev_free(thr); dev_free(thr_floor);
     dev_free(lb); dev_free(sat_pairs); dev_free(exact_ceil);
     dev_free(partial); dev_free(cand_rows); dev_free(cand_count); dev_free(flags); dev_free(cand_ip);
-    dev_free(fail_count); dev_free(fail_list); dev_free(exact_partial);
+    dev_free(fail_count); dev_free(fail_list); dev_free(state); dev_free(sat_n); dev_free(exact_partial);
     dev_free(out_ip); dev_free(out_dist); dev_free(out_labels);
     nq_cap = 0;
   }
@@ -117,6 +118,7 @@ struct b2k_index {
   int opt_tighten = 1;                        // exact-score tightening of the candidate threshold
   int opt_collect = 1;                        // K-collect serves saturated lists (else: exhaustive scan)
   int opt_inline_seed = 1;                    // single-CTA kernel: seeding inside the main launch when eligible
+  int opt_fused_tail = 1;                     // k <= 32: select + re-rank + finalize in one launch, deferred paths self-finishing
   // options
   int opt_path = 0, opt_cand_cap = kDefaultCandCap, opt_force_exact = 0, opt_scan_max_b = 0, opt_splits = 0;
   b2k_stats stats;
@@ -190,7 +192,11 @@ int ensure_workspace(b2k_index* ix, int nq, int k) {
   if ((rc = dev_alloc(&w.cand_ip, (size_t)cap * cand_cap))) return rc;
   if ((rc = dev_alloc(&w.cand_count, cap))) return rc;
   if ((rc = dev_alloc(&w.flags, cap))) return rc;
-  if ((rc = dev_alloc(&w.fail_count, 4))) return rc;      // [0] failed queries, [1] saturated pairs, [2..3] grid barrier
+  // [0] failed queries, [1] saturated pairs, [2..3] grid barrier, [4, 4+cap) K-collect items done per query,
+  // then ceil(cap/4)+1 K-exact CTAs done per group of failed queries
+  if ((rc = dev_alloc(&w.fail_count, (size_t)kCounterHead + cap + cap / 4 + 1))) return rc;
+  if ((rc = dev_alloc(&w.state, cap))) return rc;
+  if ((rc = dev_alloc(&w.sat_n, cap))) return rc;
   if ((rc = dev_alloc(&w.fail_list, cap))) return rc;
   if ((rc = dev_alloc(&w.exact_partial, (size_t)cap * exact_splits * kList))) return rc;
   if ((rc = dev_alloc(&w.exact_ceil, cap))) return rc;
@@ -222,7 +228,8 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   int rc = launch_query_prep(qp, st);
   if (rc) return rc;
   ++launches;
-  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
+  // [0] failed queries, [1] saturated pairs, [2..3] grid barrier, then per-query / per-group completion counters
+  B2K_CUDA(cudaMemsetAsync(w.fail_count, 0, (size_t)(kCounterHead + w.nq_cap + w.nq_cap / 4 + 1) * sizeof(int32_t), st));
 
   int n_lists_used = 0, split_tile_rows = 0;
   const float* eps = nullptr;
@@ -313,7 +320,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     eps = w.eps_tc;
   }
   B2K_CUDA(cudaEventRecord(ev[1], st));
-  // the select kernel reads lists [0, n_lists_used) of the stride-n_lists layout
+  // the select step reads lists [0, n_lists_used) of the stride-n_lists layout
   SelectArgs se;
   se.partial = w.partial; se.n_lists = n_lists_used; se.list_stride = w.n_lists; se.k = k; se.eps = eps;
   se.cand_cap = w.cand_cap; se.force_exact = ix->opt_force_exact;
@@ -325,49 +332,72 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   se.db_f32 = tighten ? ix->f32 : nullptr; se.q = q_dev; se.D = ix->D;
   se.lb = w.lb; se.sat_count = w.fail_count + 1; se.sat_pairs = ix->opt_collect ? w.sat_pairs : nullptr;
   se.sat_cap = ix->opt_collect ? w.sat_cap : 0;
-  rc = launch_select(se, nq, st);
-  if (rc) return rc;
-  ++launches;
 
-  if (ix->opt_collect) {
-    CollectArgs ca;
-    ca.db = ix->bf16; ca.n_rows = ix->ntotal; ca.D = ix->D; ca.Dp = ix->Dp; ca.q = q_dev; ca.lb = w.lb;
-    ca.eps = w.eps_scan; ca.sat_count = w.fail_count + 1; ca.sat_pairs = w.sat_pairs; ca.sat_cap = w.sat_cap;
-    ca.n_splits = n_lists_used; ca.tile_rows = split_tile_rows;
-    ca.cand_rows = w.cand_rows; ca.cand_count = w.cand_count; ca.flags = w.flags; ca.cand_cap = w.cand_cap;
-    rc = launch_collect(ca, ix->n_sm, st);
-    if (rc) return rc;
-    ++launches;
-  }
+  CollectArgs ca;
+  ca.db = ix->bf16; ca.n_rows = ix->ntotal; ca.D = ix->D; ca.Dp = ix->Dp; ca.q = q_dev; ca.lb = w.lb;
+  ca.eps = w.eps_scan; ca.sat_count = w.fail_count + 1; ca.sat_pairs = w.sat_pairs; ca.sat_cap = w.sat_cap;
+  ca.n_splits = n_lists_used; ca.tile_rows = split_tile_rows;
+  ca.cand_rows = w.cand_rows; ca.cand_count = w.cand_count; ca.flags = w.flags; ca.cand_cap = w.cand_cap;
 
   RerankArgs rr;
   rr.db_f32 = ix->f32; rr.q = q_dev; rr.cand_rows = w.cand_rows; rr.cand_count = w.cand_count;
   rr.cand_ip = w.cand_ip; rr.nq = nq; rr.cand_cap = w.cand_cap; rr.D = ix->D;
-  rc = launch_rerank(rr, ix->n_sm, st);
-  if (rc) return rc;
-  ++launches;
 
   FinalizeArgs fa;
   fa.cand_rows = w.cand_rows; fa.cand_count = w.cand_count; fa.cand_ip = w.cand_ip; fa.flags = w.flags;
   fa.qn2 = w.qn2; fa.norm2 = ix->norm2; fa.nq = nq; fa.cand_cap = w.cand_cap; fa.k = k;
   fa.base_offset = ix->base; fa.out_ip = ip_dev; fa.out_dist = dist_dev; fa.out_labels = labels_dev;
   fa.fail_count = w.fail_count; fa.fail_list = w.fail_list;
-  rc = launch_finalize(fa, st);
-  if (rc) return rc;
-  ++launches;
 
   ExactArgs ea;
   ea.db_f32 = ix->f32; ea.norm2 = ix->norm2; ea.n_rows = ix->ntotal; ea.D = ix->D; ea.q = q_dev;
   ea.qn2 = w.qn2; ea.nq = nq; ea.k = k; ea.base_offset = ix->base; ea.fail_count = w.fail_count;
   ea.fail_list = w.fail_list; ea.partial = w.exact_partial; ea.n_splits = w.exact_splits;
   ea.out_ip = ip_dev; ea.out_dist = dist_dev; ea.out_labels = labels_dev; ea.ceil_keys = w.exact_ceil;
-  // the exhaustive scan keeps 32 results per pass: k > 32 is served in pages, each page scanning for
-  // the rows strictly after the last result of the page before
-  for (int page = 0; page * kList < k; ++page) {
-    ea.page = page;
-    rc = launch_exact(ea, st);
+  ea.page = 0; ea.group_done = w.fail_count + kCounterHead + w.nq_cap;
+
+  if (ix->opt_fused_tail && k <= kList) {
+    // k <= 32: ONE launch per query stage instead of three (select -> re-rank -> finalize by a cluster of CTAs per
+    // query), and the two rarely needed paths finish their queries themselves (last-CTA patterns), so a search
+    // is prep, score, tail, K-collect (no-op), K-exact (no-op): 5 launches, 7 with a separate sampling pass
+    TailArgs tl;
+    tl.se = se; tl.rr = rr; tl.fa = fa; tl.state = w.state; tl.sat_n = w.sat_n;
+    rc = launch_tail(tl, nq, ix->n_sm, st);
     if (rc) return rc;
-    launches += 2;
+    ++launches;
+    if (ix->opt_collect) {
+      DeferredArgs df;
+      df.rr = rr; df.fa = fa; df.state = w.state; df.sat_n = w.sat_n; df.done = w.fail_count + kCounterHead;
+      rc = launch_collect_finish(ca, df, ix->n_sm, st);
+      if (rc) return rc;
+      ++launches;
+    }
+    rc = launch_exact_fused(ea, st);
+    if (rc) return rc;
+    ++launches;
+  } else {
+    rc = launch_select(se, nq, st);
+    if (rc) return rc;
+    ++launches;
+    if (ix->opt_collect) {
+      rc = launch_collect(ca, ix->n_sm, st);
+      if (rc) return rc;
+      ++launches;
+    }
+    rc = launch_rerank(rr, ix->n_sm, st);
+    if (rc) return rc;
+    ++launches;
+    rc = launch_finalize(fa, st);
+    if (rc) return rc;
+    ++launches;
+    // the exhaustive scan keeps 32 results per pass: k > 32 is served in pages, each page scanning for
+    // the rows strictly after the last result of the page before
+    for (int page = 0; page * kList < k; ++page) {
+      ea.page = page;
+      rc = launch_exact(ea, st);
+      if (rc) return rc;
+      launches += 2;
+    }
   }
   B2K_CUDA(cudaEventRecord(ev[2], st));
   ix->ev_head += 1;
@@ -839,6 +869,8 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
       ix->opt_collect = value != 0; return 0;
     case B2K_OPT_INLINE_SEED:
       ix->opt_inline_seed = value != 0; return 0;
+    case B2K_OPT_FUSED_TAIL:
+      ix->opt_fused_tail = value != 0; return 0;
     case B2K_OPT_SEED:
       if (value < 0 || value > 4096) break;
       ix->opt_seed = (int)value; return 0;

@@ -126,6 +126,32 @@ struct FinalizeArgs {
   int32_t* fail_list;     // [nq]
 };
 
+// Fused per-query tail (k <= 32): K-select, K-rerank and K-finalize of one query in ONE launch, by a cluster
+// of 1..8 CTAs (more CTAs per query for small batches: the re-rank is a latency-bound row gather).  Queries
+// that need more than that are left to the two deferred kernels, which exit at once when there are none:
+//   state 1: some partial list was saturated -> K-collect re-scans those splits, and the CTA that finishes
+//            the query's last work item re-ranks and finalises it on the spot (no grid-wide barrier);
+//   state 2: not certifiable (overflow, NaN bound, forced) -> fail list -> K-exact, whose last CTA per group
+//            of failed queries finalises them.
+struct TailArgs {
+  SelectArgs se;
+  RerankArgs rr;
+  FinalizeArgs fa;
+  int32_t* state;       // [nq] 0 = finished by the tail kernel, 1 = deferred to K-collect, 2 = to K-exact
+  int32_t* sat_n;       // [nq] saturated (query, list) pairs handed to K-collect
+};
+int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st);
+
+// K-collect's deferred finish: after the last (pair, sub-split) work item of a query the same CTA runs
+// K-rerank and K-finalize for it.
+struct DeferredArgs {
+  RerankArgs rr;
+  FinalizeArgs fa;
+  const int32_t* state;   // [nq]
+  const int32_t* sat_n;   // [nq]
+  int32_t* done;          // [nq] finished work items per query (zeroed per search)
+};
+
 struct ExactArgs {
   const float* db_f32;
   const float* norm2;
@@ -142,6 +168,7 @@ struct ExactArgs {
   float* out_ip; float* out_dist; int64_t* out_labels;
   unsigned long long* ceil_keys;   // [max_fail_slots] paging state: key of the last result emitted per failed slot
   int32_t page;                    // results [32*page, 32*page + 32) of every failed query
+  int32_t* group_done;             // fused form (k <= 32): [ceil(nq/4)] CTAs that finished a group's scan (zeroed per search)
 };
 
 struct MergeArgs {
@@ -164,10 +191,12 @@ int launch_scan(const ScanArgs& a, int n_queries_this_pass, cudaStream_t st);
 
 int launch_select(const SelectArgs& a, int nq, cudaStream_t st);
 int launch_collect(const CollectArgs& a, int n_sm, cudaStream_t st);
+int launch_collect_finish(const CollectArgs& a, const DeferredArgs& d, int n_sm, cudaStream_t st);   // k <= 32
 int launch_rerank(const RerankArgs& a, int n_sm, cudaStream_t st);
 int launch_finalize(const FinalizeArgs& a, cudaStream_t st);
 int exact_num_splits(int n_sm);
 int launch_exact(const ExactArgs& a, cudaStream_t st);   // scan + finalize of failed queries
+int launch_exact_fused(const ExactArgs& a, cudaStream_t st);   // k <= 32: one launch, last CTA per group finalises
 int launch_merge(const MergeArgs& a, cudaStream_t st);
 
 // K-score (tcgen05): see score_tc.cu

@@ -5,6 +5,8 @@
 //   main/search_from_image.py:322 (faiss.normalize_L2)
 // HBM-bound, one warp per row, 16-byte accesses, fixed summation order (oracle/b2k_oracle.c
 // follows the same order bit for bit).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -365,7 +367,8 @@ int launch_pack(const PackArgs& a, cudaStream_t st) {
           (reinterpret_cast<uintptr_t>(a.tables[t]) & 15) == 0;
     slots += ((a.dims[t] >> 2) + 31) >> 5;
   }
-  reg = reg && slots <= kPackSlots &&
+  static const bool two_pass = getenv("B2K_PACK_TWO_PASS") != nullptr;      // A/B switch for experiments
+  reg = reg && !two_pass && slots <= kPackSlots &&
         ((reinterpret_cast<uintptr_t>(a.out_f32) | reinterpret_cast<uintptr_t>(a.out_bf16)) & 15) == 0;
   if (reg) pack_rows_reg_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(a);
   else pack_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(a);

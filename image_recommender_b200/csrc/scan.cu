@@ -12,8 +12,9 @@
 // threshold so inserts become rare.  Only 32 records per (query, split) ever reach HBM.
 //
 // Also here: K-exact, the fp32/fp64 exhaustive scan serving queries whose certificate failed.
-#include "common.cuh"
-#include "kernels.h"
+#include <algorithm>
+
+#include "tail_common.cuh"
 #include "ptx.cuh"
 
 namespace b2k {
@@ -254,66 +255,124 @@ constexpr int kCollectSub = 64;
 constexpr int kCollectWarps = 8;
 }  // namespace
 
+// One (saturated pair, sub-split) work item: every row of the sub-split at or above the threshold is appended.
+// Returns the query of the item.  Block-wide.
+static __device__ __forceinline__ int collect_item(const CollectArgs& a, int64_t w, int64_t tiles_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_chunks = a.Dp >> 3;
+  const int2 pr = a.sat_pairs[w / kCollectSub];
+  const int sub = (int)(w % kCollectSub);
+  const int q = pr.x, split = pr.y;
+  int64_t r_begin, r_end;
+  if (a.tile_rows > 0) {
+    r_begin = (tiles_total * split / a.n_splits) * a.tile_rows;
+    r_end = min(a.n_rows, (tiles_total * (split + 1) / a.n_splits) * a.tile_rows);
+  } else {
+    r_begin = a.n_rows * (int64_t)split / a.n_splits;
+    r_end = a.n_rows * (int64_t)(split + 1) / a.n_splits;
+  }
+  const int64_t len = r_end - r_begin;
+  const int64_t s0 = r_begin + len * sub / kCollectSub, s1 = r_begin + len * (sub + 1) / kCollectSub;
+  const float thr = __fsub_rd(a.lb[q], a.eps[q]);
+  if (!(thr == thr)) {     // poisoned bound (NaN rows in the shard): only the exhaustive scan is safe
+    if (threadIdx.x == 0) atomicOr(a.flags + q, 1);
+    return q;
+  }
+  const float* __restrict__ qv = a.q + (int64_t)q * a.D;
+  const bool qvec = ((a.D & 7) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 15) == 0);
+  for (int64_t row = s0 + warp; row < s1; row += kCollectWarps) {
+    const uint4* __restrict__ x = reinterpret_cast<const uint4*>(a.db + row * a.Dp);
+    float acc = 0.f;
+    for (int c = lane; c < n_chunks; c += 32) {
+      const uint4 v = __ldcs(x + c);
+      float qf[8];
+      if (qvec && c * 8 < a.D) {
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * c);
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * c + 1);
+        qf[0] = q0.x; qf[1] = q0.y; qf[2] = q0.z; qf[3] = q0.w;
+        qf[4] = q1.x; qf[5] = q1.y; qf[6] = q1.z; qf[7] = q1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = c * 8 + j; qf[j] = i < a.D ? __ldg(qv + i) : 0.f; }
+      }
+      acc = fmaf(__uint_as_float(v.x << 16), qf[0], acc); acc = fmaf(__uint_as_float(v.x & 0xffff0000u), qf[1], acc);
+      acc = fmaf(__uint_as_float(v.y << 16), qf[2], acc); acc = fmaf(__uint_as_float(v.y & 0xffff0000u), qf[3], acc);
+      acc = fmaf(__uint_as_float(v.z << 16), qf[4], acc); acc = fmaf(__uint_as_float(v.z & 0xffff0000u), qf[5], acc);
+      acc = fmaf(__uint_as_float(v.w << 16), qf[6], acc); acc = fmaf(__uint_as_float(v.w & 0xffff0000u), qf[7], acc);
+    }
+    acc = warp_sum_f32(acc);
+    if (lane == 0 && acc >= thr) {
+      const int pos = atomicAdd(a.cand_count + q, 1);
+      if (pos < a.cand_cap) a.cand_rows[(int64_t)q * a.cand_cap + pos] = (int32_t)row;
+      else atomicOr(a.flags + q, 2);
+    }
+  }
+  return q;
+}
+
 __global__ void __launch_bounds__(kCollectWarps * 32)
 collect_kernel(CollectArgs a) {
   const int n_pairs = min(*a.sat_count, a.sat_cap);
   if (n_pairs == 0) return;
+  const int64_t tiles_total = a.tile_rows > 0 ? (a.n_rows + a.tile_rows - 1) / a.tile_rows : 0;
+  for (int64_t w = blockIdx.x; w < (int64_t)n_pairs * kCollectSub; w += gridDim.x) collect_item(a, w, tiles_total);
+}
+
+// K-collect + deferred finish (k <= 32; kernels.h: DeferredArgs): the CTA that completes the LAST work item of a
+// query (a per-query counter, no grid-wide barrier, no co-residency assumption) re-ranks the query's candidates
+// and finalises it.  Launched unconditionally behind the fused tail kernel; exits at once when no list was
+// saturated.  Dynamic shared memory: cand_cap u64 keys.
+__global__ void __launch_bounds__(kCollectWarps * 32)
+collect_finish_kernel(CollectArgs a, DeferredArgs d) {
+  extern __shared__ uint64_t fkeys[];
+  __shared__ uint64_t wtop[kCollectWarps * 32];
+  __shared__ uint64_t top[kList];
+  __shared__ int s_last;
+  const int n_pairs = min(*a.sat_count, a.sat_cap);
+  if (n_pairs == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_chunks = a.Dp >> 3;
   const int64_t tiles_total = a.tile_rows > 0 ? (a.n_rows + a.tile_rows - 1) / a.tile_rows : 0;
   for (int64_t w = blockIdx.x; w < (int64_t)n_pairs * kCollectSub; w += gridDim.x) {
-    const int2 pr = a.sat_pairs[w / kCollectSub];
-    const int sub = (int)(w % kCollectSub);
-    const int q = pr.x, split = pr.y;
-    int64_t r_begin, r_end;
-    if (a.tile_rows > 0) {
-      r_begin = (tiles_total * split / a.n_splits) * a.tile_rows;
-      r_end = min(a.n_rows, (tiles_total * (split + 1) / a.n_splits) * a.tile_rows);
-    } else {
-      r_begin = a.n_rows * (int64_t)split / a.n_splits;
-      r_end = a.n_rows * (int64_t)(split + 1) / a.n_splits;
+    const int q = collect_item(a, w, tiles_total);
+    __syncthreads();                                   // every warp's appends are issued
+    if (threadIdx.x == 0) {
+      __threadfence();                                 // ... and visible before the item counts as done
+      const int done = atomicAdd(d.done + q, 1) + 1;
+      s_last = done == d.sat_n[q] * kCollectSub;
     }
-    const int64_t len = r_end - r_begin;
-    const int64_t s0 = r_begin + len * sub / kCollectSub, s1 = r_begin + len * (sub + 1) / kCollectSub;
-    const float thr = __fsub_rd(a.lb[q], a.eps[q]);
-    if (!(thr == thr)) {     // poisoned bound (NaN rows in the shard): only the exhaustive scan is safe
-      if (threadIdx.x == 0) atomicOr(a.flags + q, 1);
+    __syncthreads();
+    if (!s_last) continue;
+    __threadfence();                                   // the other CTAs' appends of this query
+    if (d.state[q] != 1) continue;                     // already handed to K-exact by the tail kernel
+    const int flag = __ldcg(a.flags + q);
+    if (flag != 0) {                                   // overflow / poisoned bound while collecting: K-exact
+      if (threadIdx.x == 0) {
+        const int slot = atomicAdd(d.fa.fail_count, 1);
+        d.fa.fail_list[slot] = q;
+      }
       continue;
     }
-    const float* __restrict__ qv = a.q + (int64_t)q * a.D;
-    const bool qvec = ((a.D & 7) == 0) && ((reinterpret_cast<uintptr_t>(qv) & 15) == 0);
-    for (int64_t row = s0 + warp; row < s1; row += kCollectWarps) {
-      const uint4* __restrict__ x = reinterpret_cast<const uint4*>(a.db + row * a.Dp);
-      float acc = 0.f;
-      for (int c = lane; c < n_chunks; c += 32) {
-        const uint4 v = __ldcs(x + c);
-        float qf[8];
-        if (qvec && c * 8 < a.D) {
-          const float4 q0 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * c);
-          const float4 q1 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * c + 1);
-          qf[0] = q0.x; qf[1] = q0.y; qf[2] = q0.z; qf[3] = q0.w;
-          qf[4] = q1.x; qf[5] = q1.y; qf[6] = q1.z; qf[7] = q1.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const int i = c * 8 + j; qf[j] = i < a.D ? __ldg(qv + i) : 0.f; }
-        }
-        acc = fmaf(__uint_as_float(v.x << 16), qf[0], acc); acc = fmaf(__uint_as_float(v.x & 0xffff0000u), qf[1], acc);
-        acc = fmaf(__uint_as_float(v.y << 16), qf[2], acc); acc = fmaf(__uint_as_float(v.y & 0xffff0000u), qf[3], acc);
-        acc = fmaf(__uint_as_float(v.z << 16), qf[4], acc); acc = fmaf(__uint_as_float(v.z & 0xffff0000u), qf[5], acc);
-        acc = fmaf(__uint_as_float(v.w << 16), qf[6], acc); acc = fmaf(__uint_as_float(v.w & 0xffff0000u), qf[7], acc);
-      }
-      acc = warp_sum_f32(acc);
-      if (lane == 0 && acc >= thr) {
-        const int pos = atomicAdd(a.cand_count + q, 1);
-        if (pos < a.cand_cap) a.cand_rows[(int64_t)q * a.cand_cap + pos] = (int32_t)row;
-        else atomicOr(a.flags + q, 2);
-      }
-    }
+    const int cnt = min(__ldcg(a.cand_count + q), a.cand_cap);
+    rerank_query(d.rr, q, cnt, warp, kCollectWarps, lane, nullptr);
+    __syncthreads();
+    finalize_small_k(d.fa, q, cnt, fkeys, wtop, top);
+    __syncthreads();                                   // fkeys / top are reused by the next query this CTA finishes
   }
 }
 
 int launch_collect(const CollectArgs& a, int n_sm, cudaStream_t st) {
   collect_kernel<<<4 * n_sm, kCollectWarps * 32, 0, st>>>(a);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_collect_finish(const CollectArgs& a, const DeferredArgs& d, int n_sm, cudaStream_t st) {
+  static_assert(kCollectWarps * 32 == kSelThreads, "finalize_small_k strides by kSelThreads");
+  const size_t smem = (size_t)a.cand_cap * sizeof(uint64_t);
+  if (smem > 200 * 1024) { set_error("collect: %d candidate slots do not fit shared memory", a.cand_cap); return B2K_E_INVALID; }
+  if (smem > 48 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(collect_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  collect_finish_kernel<<<4 * n_sm, kCollectWarps * 32, smem, st>>>(a, d);
   B2K_CHECK_LAUNCH();
   return 0;
 }
@@ -349,10 +408,15 @@ __device__ __forceinline__ void exact_offer(float ip, int64_t row, uint64_t ceil
 // takes kExactRows rows, so each row element costs ONE fp32->fp64 conversion (the 16/clk/SM
 // conversion rate, not HBM, bounded the one-row-at-a-time form) and each staged query chunk serves
 // four rows.  The FMA order per lane is Spec R's in both forms.
+// fused (k <= 32, one page): the CTA that completes a group's scan LAST (per-group counter, no grid barrier)
+// also finalises the group's queries — K-exact is then ONE launch.  Dynamic shared memory then also holds
+// n_splits * 32 u64 keys (it is re-staged with the next group's queries afterwards).
 __global__ void __launch_bounds__(kExactWarps * 32)
-exact_scan_kernel(ExactArgs a, int q_smem) {
+exact_scan_kernel(ExactArgs a, int q_smem, int fused) {
   extern __shared__ double qd[];                                    // [kExactFQ][D] when q_smem
   __shared__ uint64_t keys[kExactFQ][kExactWarps * 32];
+  __shared__ uint64_t ftop[kList];
+  __shared__ int s_last;
   const int n_fail = *a.fail_count;
   if (n_fail == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -468,6 +532,41 @@ exact_scan_kernel(ExactArgs a, int q_smem) {
       }
     }
     __syncthreads();
+    if (!fused) continue;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(a.group_done + f0 / kExactFQ, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) continue;
+    __threadfence();
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(qd);              // the staged queries are dead for this group
+    const int M = a.n_splits * kList;
+    for (int f = 0; f < kExactFQ && f0 + f < n_fail; ++f) {
+      const int q = a.fail_list[f0 + f];
+      const Cand* src = a.partial + (int64_t)(f0 + f) * M;
+      for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const float sc = __ldcg(&src[i].score);
+        const int32_t rw = __ldcg(&src[i].row);
+        skeys[i] = cand_key(sc, rw);
+      }
+      __syncthreads();
+      block_topk_u64(skeys, M, a.k, &keys[0][0], ftop);            // keys[][]: 4 * 256 u64 >= 8 warps * 32 of scratch
+      if ((int)threadIdx.x < a.k) {
+        const uint64_t kk = ftop[threadIdx.x];
+        const int32_t row = key_row(kk);
+        float ip = -3.402823466e38f, dist = 3.402823466e38f; int64_t lab = -1;
+        if (row >= 0) {
+          ip = key_score(kk);
+          lab = a.base_offset + row;
+          dist = fmaxf(__fmaf_rn(-2.0f, ip, __fadd_rn(a.qn2[q], a.norm2[row])), 0.f);
+        }
+        if (a.out_ip) a.out_ip[(int64_t)q * a.k + threadIdx.x] = ip;
+        a.out_dist[(int64_t)q * a.k + threadIdx.x] = dist;
+        a.out_labels[(int64_t)q * a.k + threadIdx.x] = lab;
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -515,12 +614,26 @@ int launch_exact(const ExactArgs& a, cudaStream_t st) {
   const int q_smem = (a.D & 3) == 0 && q_bytes <= 160 * 1024 && (reinterpret_cast<uintptr_t>(a.db_f32) & 15) == 0;
   if (q_smem && q_bytes > 32 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_bytes));
-  exact_scan_kernel<<<a.n_splits, kExactWarps * 32, q_smem ? q_bytes : 0, st>>>(a, q_smem);
+  exact_scan_kernel<<<a.n_splits, kExactWarps * 32, q_smem ? q_bytes : 0, st>>>(a, q_smem, 0);
   B2K_CHECK_LAUNCH();
   int P = 1; while (P < a.n_splits * kList) P <<= 1;
   const size_t smem = (size_t)P * 8;
   B2K_CUDA(cudaFuncSetAttribute(exact_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   exact_finalize_kernel<<<a.nq, 512, smem, st>>>(a, P);
+  B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_exact_fused(const ExactArgs& a, cudaStream_t st) {
+  static_assert(kExactWarps * 32 == kSelThreads, "block_topk_u64 scratch is sized for kSelThreads");
+  const size_t q_bytes = (size_t)kExactFQ * a.D * sizeof(double);
+  const int q_smem = (a.D & 3) == 0 && q_bytes <= 160 * 1024 && (reinterpret_cast<uintptr_t>(a.db_f32) & 15) == 0;
+  const size_t key_bytes = (size_t)a.n_splits * kList * sizeof(uint64_t);
+  const size_t smem = std::max(q_smem ? q_bytes : (size_t)0, key_bytes);
+  if (smem > 200 * 1024 || a.k > kList) { set_error("exact: fused form needs k <= %d", (int)kList); return B2K_E_INVALID; }
+  if (smem > 32 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  exact_scan_kernel<<<a.n_splits, kExactWarps * 32, smem, st>>>(a, q_smem, 1);
   B2K_CHECK_LAUNCH();
   return 0;
 }

@@ -13,8 +13,9 @@
 //              squared-L2 distance the reference's METRIC_L2 index returns
 //              (main/create_index.py:219,230) and to global offsets.
 //   merge    : cross-shard merge of per-GPU top-k lists.
-#include "common.cuh"
-#include "kernels.h"
+#include <algorithm>
+
+#include "tail_common.cuh"
 
 namespace b2k {
 
@@ -30,103 +31,6 @@ extern "C" int b2k_debug_phase_times(unsigned long long* out) {
 #define B2K_PHASE(i) do { } while (0)
 #endif
 
-namespace {
-
-constexpr int kSelThreads = 256;
-
-__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const uint64_t u = __shfl_xor_sync(0xffffffffu, v, o);
-    v = u > v ? u : v;
-  }
-  return v;
-}
-
-// Block-cooperative top-k of n distinct non-zero u64 keys in shared memory (0 = empty slot):
-// every warp extracts the k best of its interleaved share with warp shuffles only (no block
-// barrier inside the loop), then warp 0 merges the nw*k survivors.  out[0..k) = the k largest keys,
-// descending, zero padded.  wtop: nw*32 slots of scratch.  All threads of the block must call.
-__device__ __forceinline__ void block_topk_u64(const uint64_t* keys, int n, int k, uint64_t* wtop, uint64_t* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  uint64_t prev = ~0ull;
-  for (int j = 0; j < k; ++j) {
-    uint64_t m = 0ull;
-    for (int e = warp * 32 + lane; e < n; e += nw * 32) {
-      const uint64_t v = keys[e];
-      if (v < prev && v > m) m = v;
-    }
-    m = warp_max_u64(m);
-    if (lane == 0) wtop[warp * 32 + j] = m;
-    prev = m;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    uint64_t prev2 = ~0ull;
-    for (int j = 0; j < k; ++j) {
-      uint64_t m = 0ull;
-      for (int e = lane; e < nw * k; e += 32) {
-        const uint64_t v = wtop[(e / k) * 32 + (e % k)];
-        if (v < prev2 && v > m) m = v;
-      }
-      m = warp_max_u64(m);
-      if (lane == 0) out[j] = m;
-      prev2 = m;
-    }
-  }
-  __syncthreads();
-}
-
-// Partial-list entries as distinct u64 keys: (order-preserving score key << 32) | reversed slot.
-__device__ __forceinline__ void load_list_keys(const Cand* lst, int E, uint64_t* keys) {
-  // four independent 8-byte loads in flight per thread: the lists were just written by the scoring
-  // kernel and come from L2 (a dependent one-at-a-time loop costs 6 us per 4736 entries at batch 1)
-  const int T = blockDim.x;
-  int e = threadIdx.x;
-  for (; e + 3 * T < E; e += 4 * T) {
-    Cand c[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) c[u] = lst[e + u * T];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t fk = c[u].row < 0 ? 0u : float_key(c[u].score);     // NaN scores -> 0: dropped
-      keys[e + u * T] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - (e + u * T))) : 0ull;
-    }
-  }
-  for (; e < E; e += T) {
-    const Cand c = lst[e];
-    const uint32_t fk = c.row < 0 ? 0u : float_key(c.score);
-    keys[e] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - e)) : 0ull;
-  }
-  __syncthreads();
-}
-
-}  // namespace
-
-// ---------------------------------------------------------------------------------------
-// Tightening (both branches of select_kernel): the k rows with the best approximate scores are k
-// distinct rows, so the smallest of their EXACT scores s' is a lower bound of the exact k-th best
-// score, and every row of the exact top-k has b >= s' - eps.  s' >= b_k - eps, so this threshold is
-// never looser than b_k - 2 eps and typically one eps tighter: several times fewer rows to re-rank.
-// topk[j] = j-th best key (low word = reversed slot); s_exact: k floats of scratch.  Block-wide call.
-__device__ __forceinline__ void tighten_threshold(const SelectArgs& a, int q, const Cand* lst, int E,
-                                                  const uint64_t* topk, float* s_exact, float& thr, float& lb) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* qv = a.q + (int64_t)q * a.D;
-  for (int j = warp; j < a.k; j += (kSelThreads >> 5)) {
-    const int e = E - 1 - (int)(uint32_t)(topk[j] & 0xffffffffull);
-    const float* x = a.db_f32 + (int64_t)lst[e].row * a.D;
-    const double p = lane_dot64(qv, x, a.D, lane);
-    const float sj = (float)warp_sum_f64(p);
-    if (lane == 0) s_exact[j] = sj;
-  }
-  __syncthreads();
-  float smin = INFINITY;
-  for (int j = 0; j < a.k; ++j) smin = fminf(smin, s_exact[j]);
-  const float t2 = __fsub_rd(smin, a.eps[q]);
-  if (t2 > thr) { thr = t2; lb = smin; }      // NaN-safe: keeps the looser bound
-}
-
 // One CTA per query.  Dynamic smem: k <= 32: n_lists*32 u64 keys; k > 32: P u64 keys (P = the power of
 // two >= n_lists*32, sorted in place) + n_lists ints + k floats.
 __global__ void __launch_bounds__(kSelThreads)
@@ -135,73 +39,20 @@ select_kernel(SelectArgs a, int P) {
   __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
   __shared__ uint64_t top[kList];
   __shared__ float s_exact32[kList];
-  __shared__ int s_count, s_sat;
+  __shared__ int s_ints[4];
+  int& s_count = s_ints[0];
+  int& s_sat = s_ints[1];
   const int q = blockIdx.x;
   const int E = a.n_lists * kList;
   const Cand* lst = a.partial + (int64_t)q * a.list_stride * kList;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_count = 0; s_sat = 0; }
-  B2K_PHASE(0);
-  load_list_keys(lst, E, skey);
-  B2K_PHASE(1);
-  int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
-
+  const int tid = threadIdx.x;
+  if (tid < 4) s_ints[tid] = 0;
   if (a.k <= kList) {
-    // b_k = k-th best approximate score over every list; 0: fewer than k rows listed -> everything
-    // listed is a candidate.
-    block_topk_u64(skey, E, a.k, wtop, top);
-    B2K_PHASE(2);
-    const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
-    float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
-    // lower bound of the exact k-th best score: the k best approximate rows have exact >= b_k - eps
-    float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
-    if (bk != 0u && a.db_f32 != nullptr) tighten_threshold(a, q, lst, E, top, s_exact32, thr, lb);
-
-    B2K_PHASE(3);
-    // candidates + saturation, from the shared-memory keys (rows are fetched for hits only).
-    // Warp w owns lists w, w+8, ...; lane j = entry j of the list.
-    const uint32_t thr_key = float_key(thr);              // score >= thr  <=>  key >= thr_key
-    for (int l = warp; l < a.n_lists; l += (kSelThreads >> 5)) {
-      const uint64_t key = skey[l * kList + lane];
-      const uint32_t sk = (uint32_t)(key >> 32);
-      const bool hit = sk != 0u && sk >= thr_key;
-      const unsigned hm = __ballot_sync(0xffffffffu, hit);
-      // a list whose 32 slots are all at-risk rows may hide a 33rd: K-collect re-scans that DB split
-      // for this query and lists EVERY row at or above the threshold (so nothing is emitted here);
-      // only when the pair table is full does the query fall back to the exhaustive scan
-      if (hm == 0xffffffffu) {
-        if (lane == 0) {
-          const int slot = a.sat_pairs ? atomicAdd(a.sat_count, 1) : a.sat_cap;
-          if (slot < a.sat_cap) a.sat_pairs[slot] = make_int2(q, l);
-          else s_sat = 1;
-        }
-        if (a.sat_pairs) continue;     // on pair-table overflow the query is flagged: its candidates are unused
-      }
-      if (hm) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_count, __popc(hm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (hit) {
-          const int pos = base + __popc(hm & ((1u << lane) - 1u));
-          if (pos < a.cand_cap) out_rows[pos] = lst[l * kList + lane].row;
-        }
-      }
-    }
-    __syncthreads();
-    B2K_PHASE(4);
-    if (tid == 0) {
-      int cnt = s_count;
-      int flag = 0;
-      if (s_sat) flag |= 1;                       // a list may hide at-risk rows
-      if (cnt > a.cand_cap) { flag |= 2; cnt = a.cand_cap; }
-      if (a.force_exact) flag |= 4;
-      a.cand_count[q] = cnt;
-      a.flags[q] = flag;
-      a.thr[q] = thr;
-      a.lb[q] = lb;
-    }
+    select_small_k(a, q, skey, wtop, top, s_exact32, s_ints);     // first barrier inside: after the key load
     return;
   }
+  load_list_keys(lst, E, skey);
+  int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
 
   // ---- k > 32: sort every listed entry; the candidates are a prefix of the sorted keys
   int* l_cnt = reinterpret_cast<int*>(skey + P);                 // [n_lists] entries at or above the threshold
@@ -251,6 +102,64 @@ select_kernel(SelectArgs a, int P) {
     a.thr[q] = thr;
     a.lb[q] = lb;
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused tail, k <= 32 (kernels.h: TailArgs).  Cluster of C CTAs per query (gridDim.x = nq * C):
+//   rank 0   : K-select -> candidates, flags, state
+//   all ranks: K-rerank, warp (rank, w) takes candidates rank * 8 + w, + 8 C, ...
+//   rank 0   : K-finalize
+// Dynamic shared memory: max(n_lists * 32, cand_cap) u64 keys, then (q_smem) D doubles.
+__global__ void __launch_bounds__(kSelThreads)
+tail_kernel(TailArgs t, int key_slots, int q_smem) {
+  extern __shared__ uint64_t skey[];
+  __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
+  __shared__ uint64_t top[kList];
+  __shared__ float s_exact32[kList];
+  __shared__ int s_ints[4];
+  unsigned int rank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const int q = blockIdx.x / (int)csize;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int state = 0;
+  if (rank == 0) {
+    if (tid < 4) s_ints[tid] = 0;
+    const int flag = select_small_k(t.se, q, skey, wtop, top, s_exact32, s_ints);
+    state = flag != 0 ? 2 : (s_ints[2] > 0 ? 1 : 0);
+    if (tid == 0) {
+      t.state[q] = state;
+      t.sat_n[q] = s_ints[2];
+      if (state == 2) {                       // K-exact serves it: register it right away
+        const int slot = atomicAdd(t.fa.fail_count, 1);
+        t.fa.fail_list[slot] = q;
+      }
+    }
+  }
+  if (csize > 1) {
+    // rank 0's candidate list / state -> the other CTAs of the cluster (release / acquire at cluster scope)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (rank != 0) state = __ldcg(t.state + q);
+  }
+  if (state != 0) return;                     // uniform over the cluster
+  const int cnt = min(__ldcg(t.rr.cand_count + q), t.rr.cand_cap);
+  double* qd = nullptr;
+  if (q_smem) {
+    qd = reinterpret_cast<double*>(skey + key_slots);
+    const float* qv = t.rr.q + (int64_t)q * t.rr.D;
+    for (int i = tid; i < t.rr.D; i += kSelThreads) qd[i] = (double)__ldg(qv + i);
+    __syncthreads();
+  }
+  rerank_query(t.rr, q, cnt, (int)rank * (kSelThreads >> 5) + warp, (int)csize * (kSelThreads >> 5), lane, qd);
+  if (csize > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (rank != 0) return;
+  } else {
+    __syncthreads();
+  }
+  finalize_small_k(t.fa, q, cnt, skey, wtop, top);
 }
 
 // One CTA per query: admission floor for the full pass from the lists of the sampling pass.
@@ -422,6 +331,33 @@ int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
     B2K_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   select_kernel<<<nq, kSelThreads, smem, st>>>(a, P);
   B2K_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st) {
+  const int E = a.se.n_lists * kList;
+  const int key_slots = std::max(E, (int)a.fa.cand_cap);
+  // small batches: up to 8 CTAs share one query's row gathers; large ones: one CTA per query, the query widened
+  // to fp64 in shared memory (halves the conversions of a throughput-bound re-rank, as in rerank_kernel)
+  int csize = 1;
+  while (csize < 8 && nq * csize * 2 <= 4 * n_sm) csize *= 2;
+  const size_t q_bytes = (size_t)a.rr.D * sizeof(double);
+  const int q_smem = csize == 1 && nq >= 8 * n_sm && (a.rr.D & 3) == 0 && q_bytes <= 64 * 1024 &&
+                     ((reinterpret_cast<uintptr_t>(a.rr.db_f32) | reinterpret_cast<uintptr_t>(a.rr.q)) & 15) == 0;
+  const size_t smem = (size_t)key_slots * sizeof(uint64_t) + (q_smem ? q_bytes : 0);
+  if (smem > 200 * 1024) { set_error("tail: %d key slots do not fit shared memory", key_slots); return B2K_E_INVALID; }
+  if (smem > 48 * 1024)
+    B2K_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nq * csize), 1, 1);
+  cfg.blockDim = dim3(kSelThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = (unsigned)csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  B2K_CUDA(cudaLaunchKernelEx(&cfg, tail_kernel, a, key_slots, q_smem));
   return 0;
 }
 

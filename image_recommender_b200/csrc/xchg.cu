@@ -41,6 +41,7 @@ xchg_push_kernel(XchgPeers peers, XchgLayout lay, int rank, int parity, unsigned
     const int64_t l = lab[e];
     for (int g = 0; g < lay.world; ++g) {
       unsigned char* b = peers.base[g];
+      if (!b) continue;                 // not a target (single-process groups merge on the root only)
       reinterpret_cast<float*>(b + lay.ip_off(parity, rank))[e] = a;
       reinterpret_cast<float*>(b + lay.dist_off(parity, rank))[e] = d;
       reinterpret_cast<int64_t*>(b + lay.lab_off(parity, rank))[e] = l;
@@ -54,6 +55,7 @@ xchg_push_kernel(XchgPeers peers, XchgLayout lay, int rank, int parity, unsigned
       *done_ctas = 0u;
       __threadfence_system();
       for (int g = 0; g < lay.world; ++g) {
+        if (!peers.base[g]) continue;
         unsigned long long* f = reinterpret_cast<unsigned long long*>(peers.base[g] + lay.flag_off(parity, rank));
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
       }

@@ -51,6 +51,8 @@ typedef struct b2k_index b2k_index;
                                  /* batches of 32 queries and more), 0 off, 2 always                           */
 #define B2K_OPT_COLLECT       9  /* saturated partial lists are re-scanned by K-collect: 1 on (default), 0 = exhaustive scan */
 #define B2K_OPT_INLINE_SEED  10  /* <= 128 queries: seeding folded into the scoring launch (grid barrier): 1 on (default) */
+#define B2K_OPT_FUSED_TAIL   11  /* k <= 32: select + re-rank + finalize as ONE launch (cluster of CTAs per query), K-collect and  */
+                                 /* K-exact finish their queries themselves: 1 on (default), 0 = one launch per stage (as k > 32) */
 #define B2K_OPT_SEED          7  /* K-score threshold seeding: 1 auto (default), 0 off, N > 1 = a sampling pass of  */
                                  /* N tiles per split (forces the three-launch form, no in-kernel seeding)        */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs above 128 queries unless the last 256-query */
@@ -201,6 +203,35 @@ int  b2k_xchg_merge(b2k_xchg* x, int32_t nq, int32_t k, float* out_ip, float* ou
  * resident index survives).  *timed_out_ranks: bit g = rank g was missing; returns B2K_E_PEER when non-zero
  * (the bits are cleared by the call). */
 int  b2k_xchg_status(b2k_xchg* x, uint32_t* timed_out_ranks);
+
+/* ---- several GPUs, ONE process ---------------------------------------------------------------------------
+ * The reference's CLI / ImageRecommender is a single process (main/search_from_image.py:430-441): a b2k_group
+ * drives the row shards on n_devices GPUs of the box from the one calling thread (internally one worker thread
+ * per device; the devices' results travel to the first device over NVLink peer memory and are merged there) —
+ * no process group, no NCCL, no IPC handles.  devices == NULL: 0 .. n_devices-1.
+ *   load()         every device loads ITS contiguous row range of the index file (rows ceil(n/G) * r ...)
+ *   set_shard()    or: adopt shards created by the caller (one per rank, base offsets = their row ranges)
+ *   search()       = put_queries (H2D to every device) + run (local search, exchange, merge; synchronous)
+ *                    + get_results (D2H from the first device); the three steps are exposed so that a caller
+ *                    can keep the queries resident, as bench.py does
+ *   search_groups()  b2k_search_groups over the group. */
+typedef struct b2k_group b2k_group;
+int  b2k_group_create(const int32_t* devices, int32_t n_devices, b2k_group** out);
+void b2k_group_destroy(b2k_group* g);
+int32_t b2k_group_size(const b2k_group* g);
+int  b2k_group_load(b2k_group* g, const char* path);
+int  b2k_group_set_shard(b2k_group* g, int32_t rank, b2k_index* shard);     /* not owned by the group */
+b2k_index* b2k_group_shard(b2k_group* g, int32_t rank);
+int64_t b2k_group_ntotal(const b2k_group* g);
+int32_t b2k_group_dim(const b2k_group* g);
+int  b2k_group_search(b2k_group* g, const float* q_host, int32_t nq, int32_t k, float* dist_host,
+                      int64_t* labels_host, float* ip_host);
+int  b2k_group_put_queries(b2k_group* g, const float* q_host, int32_t nq, int32_t k);
+int  b2k_group_run(b2k_group* g, int32_t nq, int32_t k);
+int  b2k_group_get_results(b2k_group* g, float* dist_host, int64_t* labels_host, float* ip_host);
+int  b2k_group_search_groups(b2k_group* g, const float* parts_host, int64_t n_images, const int32_t* group_offsets,
+                             int32_t n_groups, int32_t k, float* dist_host, int64_t* labels_host, float* ip_host);
+int  b2k_group_last_run_ms(const b2k_group* g, float* max_ms);   /* device time of the last run(), max over devices */
 
 /* Replaces faiss.normalize_L2(x) (main/search_from_image.py:322): in place on a host
  * array, rows with zero norm untouched; computed on `device`. */

@@ -57,7 +57,10 @@ class ImageRecommender:
         if not use_gpu:
             raise ValueError("this engine is GPU-only (no CPU search path); use_gpu=False is not supported")
         self.use_gpu = use_gpu
-        self.device = device
+        # device: a CUDA ordinal, or "all": the index is row-sharded over every GPU of the box and driven from this
+        # one process (image_recommender_b200.ShardGroup; no torchrun)
+        self.device = 0 if device == "all" else int(device)
+        self.all_devices = device == "all"
         # extractor settings are accepted for signature compatibility only
         self.sift_codebook_path = Path(sift_codebook_path).expanduser().resolve()
         self.sift_pca_path = Path(sift_pca_path).expanduser().resolve()
@@ -396,6 +399,9 @@ class ImageRecommender:
         except Exception:
             sharded = False
         if not sharded:
+            if self.all_devices:
+                from image_recommender_b200 import ShardGroup
+                return ShardGroup.load(f)
             return FlatShard.load(f, device=self.device)
         from image_recommender_b200.sharded import ShardedIndex
         return ShardedIndex.load(f, device=self.device)
@@ -466,7 +472,8 @@ def main(argv=None):
     ap.add_argument("--index", default="color", help="e.g. combo_color_sift_dreamsim or color,sift")
     ap.add_argument("--top-k", type=int, default=5)
     ap.add_argument("--index-dir", default=".")
-    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--device", default="0", help="CUDA ordinal, or 'all': row-shard the index over every GPU of the "
+                                                     "box from this one process (no torchrun)")
     ap.add_argument("--plot", action="store_true")
     a = ap.parse_args(argv)
     if not a.serve and not a.query:
@@ -480,7 +487,7 @@ def main(argv=None):
         torch.cuda.set_device(a.device)
         dist.init_process_group("nccl", device_id=torch.device("cuda", a.device))
     rec = ImageRecommender(images_root=a.images_root, db_path=a.db_path, top_k=a.top_k, index_dir=a.index_dir,
-                           device=a.device)
+                           device=a.device if a.device == "all" else int(a.device))
     def answer(paths):
         res = rec.search_similar_images(paths, index_type=a.index, plot=a.plot and rank == 0)
         if rank == 0:

@@ -171,3 +171,133 @@ def test_search_groups_equals_host_mean_normalise_search(gpu, dims, n):
     with pytest.raises(irb.B2KError):
         ix.search_groups(imgs, np.array([0, 3, 3, imgs.shape[0]], np.int32), 10)       # an empty group
     ix.close()
+
+
+def test_fused_tail_equals_staged_tail(gpu):
+    """B2K_OPT_FUSED_TAIL: the one-launch tail (cluster of CTAs per query: select -> re-rank -> finalize; K-collect
+    and K-exact finishing their queries themselves) returns the bits of the one-launch-per-stage pipeline and of
+    the oracle — plain queries, a near-duplicate burst (saturated lists -> K-collect), forced-exact queries and a
+    candidate-budget overflow — and launches at most 5 kernels per search at batch 1."""
+    import image_recommender_b200 as irb
+    from image_recommender_b200 import _capi
+    n = 30000
+    tabs, _ = _mk(n)
+    for t in tabs:                       # a run of 300 near-duplicates of row 1000, stored next to each other
+        t[2000:2300] = t[1000] * (1.0 + 1e-4 * np.arange(300, dtype=np.float32)[:, None])
+    pk = oracle.pack(tabs)
+    ix = irb.FlatShard(DIMS, n, device=gpu)
+    ix.add_tables(tabs)
+    q = oracle.synth_queries(DIMS, 700, n, n_clusters=8)
+    q[5] = pk["f32"][2100] / np.sqrt(3.0)         # lands in the burst
+    q[41] = pk["f32"][2299] / np.sqrt(3.0)
+    for nq in (1, 7, 42, 130, 700):
+        w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q[:nq], 10, pk["norm2"])
+        res = {}
+        for fused in (1, 0):
+            ix.set_option(_capi.OPT_FUSED_TAIL, fused)
+            res[fused] = ix.search_ip(q[:nq], 10)
+            st = ix.stats()
+            if fused and nq == 1:
+                assert st["launches"] <= 5, st
+            if nq >= 7:
+                assert st["n_saturated"] > 0          # the burst saturates lists: K-collect ran
+        for a, b in zip(res[1], res[0]):
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                  b.view(np.uint32) if b.dtype == np.float32 else b)
+        assert np.array_equal(res[1][1], w_lab)
+        assert np.array_equal(res[1][2].view(np.uint32), w_ip.view(np.uint32))
+        assert np.array_equal(res[1][0].view(np.uint32), w_dist.view(np.uint32))
+    ix.set_option(_capi.OPT_FUSED_TAIL, 1)
+    w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q[:50], 10, pk["norm2"])
+    for key, val in ((_capi.OPT_FORCE_EXACT, 1), (_capi.OPT_RERANK, 32), (_capi.OPT_COLLECT, 0)):
+        ix.set_option(key, val)
+        dist, lab, ip = ix.search_ip(q[:50], 10)
+        assert ix.stats()["n_uncertified"] > 0
+        assert np.array_equal(lab, w_lab) and np.array_equal(ip.view(np.uint32), w_ip.view(np.uint32))
+        ix.set_option(key, 1 if key == _capi.OPT_COLLECT else 0)
+    ix.close()
+
+
+def _group_devices():
+    """Two ranks: two GPUs when the box has them, else both on device 0 (the group logic is the same; the
+    exchange then runs between two streams of one device)."""
+    import image_recommender_b200 as irb
+    return [0, 1] if irb.device_count() >= 2 else [0, 0]
+
+
+def test_shard_group_single_process_equals_single_shard(gpu, tmp_path):
+    """b2k_group (one process driving several row shards: worker thread per rank, peer-memory push to the root,
+    merge there) returns exactly what ONE shard holding all rows returns — adopted shards and b2k_group_load of
+    an index file alike, plain queries and query groups."""
+    import image_recommender_b200 as irb
+    n = 9001
+    tabs, pk = _mk(n)
+    whole = irb.FlatShard(DIMS, n, device=gpu)
+    whole.add_tables(tabs)
+    f = tmp_path / "index_hnsw_color_sift_dreamsim.faiss"
+    whole.save(str(f), ids=np.arange(n))
+    q = oracle.synth_queries(DIMS, 150, n, n_clusters=8)
+    devs = _group_devices()
+    from image_recommender_b200.sharded import shard_range
+    grp = irb.ShardGroup(devs)
+    shards = []
+    for r, dev in enumerate(devs):
+        r0, r1 = shard_range(n, len(devs), r)
+        s = irb.FlatShard(DIMS, r1 - r0, device=dev, base_offset=r0)
+        s.add_tables([t[r0:r1] for t in tabs])
+        shards.append(s)
+    grp.set_shards(shards)
+    loaded = irb.ShardGroup.load(str(f), devs)
+    assert grp.ntotal == n and loaded.ntotal == n and loaded.d == sum(DIMS)
+    for nq, k in ((1, 10), (7, 5), (150, 10), (33, 40)):
+        want = whole.search_ip(q[:nq], k)
+        w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q[:nq], k, pk["norm2"])
+        assert np.array_equal(want[1], w_lab)
+        for g in (grp, loaded):
+            got = g.search_ip(q[:nq], k)
+            assert np.array_equal(got[1], want[1])
+            assert np.array_equal(got[2].view(np.uint32), want[2].view(np.uint32))
+            assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32))
+    offs = np.array([0, 1, 4, 6, 11], np.int32)
+    a = whole.search_groups(q[:11], offs, 10)
+    b = loaded.search_groups(q[:11], offs, 10)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
+    # resident-query form used by bench.py --single-process
+    grp.put_queries(q[:64], 10)
+    grp.run(64, 10)
+    assert grp.last_run_ms() > 0
+    got = grp.get_results(64, 10)
+    want = whole.search_ip(q[:64], 10)
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2].view(np.uint32), want[2].view(np.uint32))
+    loaded.close()
+    grp.close()
+    whole.close()
+
+
+def test_image_recommender_device_all(gpu, tmp_path, monkeypatch):
+    """ImageRecommender(device='all'): the README flow on every visible GPU from one process, same hits as one GPU."""
+    import sqlite3
+    import pickle
+    from main.create_index import FAISSIndexBuilderDB
+    from main.search_from_image import ImageRecommender
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "image_data").mkdir()
+    rng = np.random.default_rng(3)
+    con = sqlite3.connect("images.db")
+    con.executescript("CREATE TABLE images (id INTEGER PRIMARY KEY, path TEXT);"
+                      "CREATE TABLE color_vectors (image_id INTEGER PRIMARY KEY, color_vector_blob BLOB);")
+    for i in range(1, 301):
+        v = np.abs(rng.normal(size=48)).astype(np.float32)
+        con.execute("INSERT INTO images VALUES (?, ?)", (i, f"image_data/img_{i:04d}.jpg"))
+        con.execute("INSERT INTO color_vectors VALUES (?, ?)", (i, sqlite3.Binary(pickle.dumps(v / np.linalg.norm(v), protocol=pickle.HIGHEST_PROTOCOL))))
+    con.commit()
+    con.close()
+    FAISSIndexBuilderDB(db_path="images.db", vector_types=["color"], log_dir=str(tmp_path / "logs")).build_index()
+    one = ImageRecommender(images_root="image_data", db_path="images.db", top_k=5, device=0)
+    many = ImageRecommender(images_root="image_data", db_path="images.db", top_k=5, device="all")
+    for i in (1, 57, 300):
+        qp = [str(tmp_path / "image_data" / f"img_{i:04d}.jpg")]
+        a, b = one.search_similar_images(qp, "color"), many.search_similar_images(qp, "color")
+        assert a == b and a[0][0].name == f"img_{i:04d}.jpg"
+    one.close()
+    many.close()
