@@ -92,6 +92,9 @@ def parse_args():
                          "about 30 s (2500 rows per core, at most 50000); 0: off")
     ap.add_argument("--cpu-rows", type=int, default=400_000)
     ap.add_argument("--cpu-batch", type=int, default=0, help="queries of the CPU sample (default: the step's batch, <= 4096)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N > 1 without torchrun: ONE process drives the N row shards through b2k_group (worker thread per "
+                         "GPU inside the library, NVLink peer-memory exchange to GPU 0); same workload, same JSON line")
     ap.add_argument("--selfcheck", type=int, default=64,
                     help="queries of the headline batch re-run with the exhaustive fp32 scan on every rank and compared "
                          "bit for bit with the certified path's output (0: off)")
@@ -339,8 +342,108 @@ def host_merge(g_dist, g_lab, g_ip, k):
     return torch.gather(dist, 1, order), torch.gather(lab, 1, order), torch.gather(ip, 1, order)
 
 
+def run_single_process(args):
+    """--single-process: the N-GPU workload driven by ONE process through b2k_group (include/b2k.h): what
+    ImageRecommender(device="all") and the CLI use.  Timed by the host clock around K back-to-back
+    b2k_group_run calls with the queries resident on every GPU (each call: local searches on all GPUs in
+    parallel, peer-memory push to GPU 0, merge there, synchronised) — host-side thread wake-ups included."""
+    import numpy as np
+    import torch
+    import image_recommender_b200 as irb
+    from image_recommender_b200 import _capi
+    from image_recommender_b200.sharded import shard_range
+    N = args.gpus
+    peaks = load_peaks()
+    n_total, B, k = args.rows, args.batch, args.k
+    shards = []
+    t0 = time.perf_counter()
+    for r in range(N):
+        r0, r1 = shard_range(n_total, N, r)
+        s = irb.FlatShard(DIMS, r1 - r0, device=r, base_offset=r0)
+        s.fill_synthetic(r1 - r0, total_rows=n_total)
+        shards.append(s)
+    build_s = time.perf_counter() - t0
+    n_local = shards[0].ntotal
+    grp = irb.ShardGroup(list(range(N)))
+    grp.set_shards(shards)
+    torch.cuda.set_device(0)
+    q_host = shards[0].synth_queries_device(B, total_rows=n_total).cpu().numpy()
+
+    def timed(q, steps, warmup):
+        grp.put_queries(q, k)
+        for _ in range(warmup):
+            grp.run(q.shape[0], k)
+        for s in shards:
+            s.stats()
+        dev_ms = 0.0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            grp.run(q.shape[0], k)
+            dev_ms += grp.last_run_ms()
+        dt = (time.perf_counter() - t0) / steps
+        return dt * 1e3, dev_ms / steps, shards[0].stats()
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_step, dev_ms, st = timed(q_host, args.steps, args.warmup)
+    clocks = sampler.stop()
+    certified = grp.get_results(B, k)
+    # e2e: host buffers in, host buffers out, every step
+    for _ in range(args.warmup):
+        grp.search_ip(q_host, k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        grp.search_ip(q_host, k)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    ms_b1, dev_b1, st1 = timed(q_host[:1], max(args.steps, 20), max(args.warmup, 5))
+    selfcheck = None
+    if args.selfcheck > 0:
+        nsc = min(args.selfcheck, B)
+        idx = np.round(np.linspace(0, B - 1, nsc)).astype(np.int64)
+        for s in shards:
+            s.set_option(_capi.OPT_FORCE_EXACT, 1)
+        exact = grp.search_ip(q_host[idx], k)
+        for s in shards:
+            s.set_option(_capi.OPT_FORCE_EXACT, 0)
+        ok = all(np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                b[idx].view(np.uint32) if b.dtype == np.float32 else b[idx]) for a, b in zip(exact, certified))
+        selfcheck = {"queries": nsc, "equal": bool(ok), "ranks": N,
+                     "what": "FORCE_EXACT on every shard, merged by the group, vs the certified headline output (bit for bit)"}
+    flops = 2.0 * B * n_local * D
+    tc_ach = flops / (st["score_ms"] * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": B / ms_step * 1e3, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "mode": "single-process (b2k_group)",
+        "config": {"workload": f"{args.workload_name} D={D}, {n_total} rows row-sharded over {N} GPU(s) ({n_local} rows/GPU), "
+                               f"batch {B}, top-{k}, exact; ONE process, b2k_group",
+                   "timing": "host clock around K b2k_group_run calls (queries resident); device_ms_per_step = CUDA events, max over GPUs",
+                   "batch": B, "k": k, "rows": n_total},
+        "device_ms_per_step": dev_ms,
+        "roofline": {"bound": "tensor", "achieved": tc_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": tc_ach / peaks["bf16_tflops"], "kernel": {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel", 4: "score_tn_kernel"}[st["path"]],
+                     "kernel_ms": st["score_ms"], "traffic": None, "algorithmic_flops_per_launch": flops, "gpu": 0},
+        "roofline_b1": {"bound": "hbm", "achieved": 2.0 * n_local * D / (st1["score_ms"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": 2.0 * n_local * D / (st1["score_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "kernel_ms": st1["score_ms"],
+                        "ms_per_query": ms_b1, "device_ms_per_query": dev_b1, "launches_per_query": st1["launches"] + (2 if N > 1 else 0)},
+        "cpu_baseline": None,
+        "e2e": {"value": B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(q_host.nbytes) * N, "d2h_bytes_per_step": B * k * 16},
+        "gpu_launches": args.steps * N * (st["launches"] + (2 if N > 1 else 0)),
+        "clocks": clocks,
+        "extra": {"selfcheck": selfcheck, "launches_per_step": st["launches"], "build_rows_per_s": n_total / build_s,
+                  "uncertified_queries": max(st["n_uncertified"], 0)},
+    }
+    print(json.dumps(line), flush=True)
+    grp.close()
+    if selfcheck is not None and not selfcheck["equal"]:
+        sys.exit(3)
+
+
 def main():
     args = parse_args()
+    if args.single_process and args.impl == "b200":
+        run_single_process(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -486,7 +589,7 @@ def main():
             dt = float(t.item())
         return dt, q_host.numel() * 4, out_d.numel() * 4 + out_l.numel() * 8
 
-    KNAME = {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel"}
+    KNAME = {1: "scan_bf16_kernel", 2: "score_tc_kernel", 3: "score_tc2_kernel", 4: "score_tn_kernel"}
 
     # ---- headline: batch B
     qd = shard.synth_queries_device(B, total_rows=n_total)

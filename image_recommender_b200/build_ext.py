@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libb2k.so"
-SOURCES = ["api.cu", "pack.cu", "scan.cu", "score_tc.cu", "score_tc2.cu", "select.cu", "xchg.cu", "ingest.cu", "group.cu"]
+SOURCES = ["api.cu", "pack.cu", "scan.cu", "score_tc.cu", "score_tc2.cu", "score_tn.cu", "select.cu", "xchg.cu", "ingest.cu", "group.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -109,7 +109,10 @@ struct b2k_index {
   bool pin_busy[2] = {false, false};
   Workspace ws;
   // TMA descriptors (host copies; passed by value at launch)
-  alignas(64) CUtensorMap tmap_q, tmap_db, tmap_db2;   // tmap_db2: 128-row boxes for the CTA-pair kernel
+  alignas(64) CUtensorMap tmap_q, tmap_db, tmap_db2;   // tmap_db2: 128-row boxes for the CTA-pair kernels
+  alignas(64) CUtensorMap tmap_qn;                     // queries as the N operand of the transposed kernel
+  const void* tmap_qn_ptr = nullptr; int tmap_qn_rows = 0, tmap_qn_n16 = 0;
+  int opt_tn = -1;                                     // transposed kernel: -1 auto, 0 never, 1 whenever it applies
   const void* tmap_q_ptr = nullptr; int tmap_q_rows = 0;
   const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
   int coresident[2] = {-1, -1};               // CTAs of score_tc / score_tc2 resident at once (occupancy query, lazily)
@@ -289,12 +292,18 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // One query tile on the single-CTA kernel = one resident CTA per split: the sampling pass, the seed
     // kernel and the re-read of the sampled tiles fold into the main launch (in-kernel seeding).
     // (CTA pairs: up to 256 queries when the pairs of one query tile fill at most one wave.)
+    // Transposed kernel (score_tn.cu): tensor work proportional to the live queries and an epilogue thread per DB
+    // row.  Auto: (a) 129..240 queries, where the M = queries kernels pay for 256; (b) narrow rows at small
+    // batches on long shards, where their 256-column drain per tile is the bound.  It runs behind a seeded floor.
+    const bool tn_ok = k <= kList && score_tn_supports(ix->Dp, nq) && (ix->n_sm & ~1) <= w.n_lists && forced == 0;
+    const bool tn_auto = seed && ((nq > 128 && nq <= 240) || (ix->Dp <= 256 && nq <= 64 && tiles_per_split >= 64));
+    const bool use_tn = tn_ok && (ix->opt_tn > 0 || (ix->opt_tn < 0 && tn_auto));
     // The grid barrier needs every CTA resident: the grid must fit what the occupancy query says this device
     // holds at once (the barrier itself is bounded in time should that still fail at run time).
     const int n_ctas = pair ? 2 * ta.plan.n_splits : ta.plan.n_splits;
     int& resident = ix->coresident[pair ? 1 : 0];
     if (resident < 0) resident = pair ? score_tc2_max_coresident(ix->n_sm) : score_tc_max_coresident(ix->n_sm);
-    if (seed && ix->opt_inline_seed && ix->opt_seed == 1 && k <= kList && ta.plan.n_qtiles == 1 &&
+    if (!use_tn && seed && ix->opt_inline_seed && ix->opt_seed == 1 && k <= kList && ta.plan.n_qtiles == 1 &&
         n_ctas <= resident && ta.plan.n_splits <= 160 && nq <= (pair ? 2 : 1) * n_ctas) {
       ta.seed_k = k;
       seed = false;
@@ -311,12 +320,29 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
       launches += 2;
       ta.max_tiles = 0; ta.thr_floor = w.thr_floor;
     }
-    rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
-    if (rc) return rc;
-    ++launches;
-    path = pair ? 3 : 2;
-    n_lists_used = ta.plan.n_splits;
-    split_tile_rows = score_tc_tile_rows();
+    if (use_tn) {
+      // main pass on the transposed kernel (queries on N); the floor comes from the sampling pass above
+      if (ix->tmap_qn_ptr != w.q_bf16 || ix->tmap_qn_rows != nq_pad || ix->tmap_qn_n16 != score_tn_n16(nq)) {
+        rc = score_tn_encode_q_map(&ix->tmap_qn, w.q_bf16, nq_pad, ix->Dp, nq);
+        if (rc) return rc;
+        ix->tmap_qn_ptr = w.q_bf16; ix->tmap_qn_rows = nq_pad; ix->tmap_qn_n16 = score_tn_n16(nq);
+      }
+      ta.tmap_q = &ix->tmap_qn; ta.tmap_db = &ix->tmap_db2;
+      ta.plan = score_tn_plan(nq, ix->ntotal, ix->n_sm);
+      rc = launch_score_tn(ta, st);
+      if (rc) return rc;
+      ++launches;
+      path = 4;
+      n_lists_used = ta.plan.n_splits;
+      split_tile_rows = score_tn_tile_rows();
+    } else {
+      rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
+      if (rc) return rc;
+      ++launches;
+      path = pair ? 3 : 2;
+      n_lists_used = ta.plan.n_splits;
+      split_tile_rows = score_tc_tile_rows();
+    }
     eps = w.eps_tc;
   }
   B2K_CUDA(cudaEventRecord(ev[1], st));
@@ -871,6 +897,9 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
       ix->opt_inline_seed = value != 0; return 0;
     case B2K_OPT_FUSED_TAIL:
       ix->opt_fused_tail = value != 0; return 0;
+    case B2K_OPT_TN:
+      if (value < -1 || value > 1) break;
+      ix->opt_tn = (int)value; return 0;
     case B2K_OPT_SEED:
       if (value < 0 || value > 4096) break;
       ix->opt_seed = (int)value; return 0;

@@ -149,6 +149,44 @@ __device__ __forceinline__ double lane_dot64(const float* __restrict__ q, const 
   return p;
 }
 
+// Two candidate rows at once against one query: the query chunk is loaded and widened once, sixteen 16-byte row
+// loads per lane are in flight instead of eight (the re-rank of a small batch is a chain of latency-bound row
+// gathers: half the rounds).  Per row the FMA order is exactly lane_dot64's.
+__device__ __forceinline__ void lane_dot64_x2(const float* __restrict__ q, const float* __restrict__ x0,
+                                              const float* __restrict__ x1, int d, int lane, double& p0, double& p1) {
+  p0 = 0.0; p1 = 0.0;
+  const bool vec = ((d & 3) == 0) && (((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(x0) |
+                                        reinterpret_cast<uintptr_t>(x1)) & 15) == 0);
+  if (!vec) { p0 = lane_dot64(q, x0, d, lane); p1 = lane_dot64(q, x1, d, lane); return; }
+  const float4* a4 = reinterpret_cast<const float4*>(x0);
+  const float4* b4 = reinterpret_cast<const float4*>(x1);
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  const int n4 = d >> 2;
+  int i = lane;
+  for (; i + 7 * 32 < n4; i += 8 * 32) {
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { va[u] = __ldg(a4 + i + u * 32); vb[u] = __ldg(b4 + i + u * 32); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 w = __ldg(q4 + i + u * 32);
+      const double wx = (double)w.x, wy = (double)w.y, wz = (double)w.z, ww = (double)w.w;
+      p0 = __fma_rn(wx, (double)va[u].x, p0); p0 = __fma_rn(wy, (double)va[u].y, p0);
+      p0 = __fma_rn(wz, (double)va[u].z, p0); p0 = __fma_rn(ww, (double)va[u].w, p0);
+      p1 = __fma_rn(wx, (double)vb[u].x, p1); p1 = __fma_rn(wy, (double)vb[u].y, p1);
+      p1 = __fma_rn(wz, (double)vb[u].z, p1); p1 = __fma_rn(ww, (double)vb[u].w, p1);
+    }
+  }
+  for (; i < n4; i += 32) {
+    const float4 va = __ldg(a4 + i), vb = __ldg(b4 + i), w = __ldg(q4 + i);
+    const double wx = (double)w.x, wy = (double)w.y, wz = (double)w.z, ww = (double)w.w;
+    p0 = __fma_rn(wx, (double)va.x, p0); p0 = __fma_rn(wy, (double)va.y, p0);
+    p0 = __fma_rn(wz, (double)va.z, p0); p0 = __fma_rn(ww, (double)va.w, p0);
+    p1 = __fma_rn(wx, (double)vb.x, p1); p1 = __fma_rn(wy, (double)vb.y, p1);
+    p1 = __fma_rn(wz, (double)vb.z, p1); p1 = __fma_rn(ww, (double)vb.w, p1);
+  }
+}
+
 // Same arithmetic with the query already widened to fp64 (shared memory): one fp32->fp64 conversion per
 // element instead of two — the conversion rate (16/clk/SM), not HBM, bounds a throughput-bound re-rank.
 __device__ __forceinline__ double lane_dot64_qd(const double* __restrict__ qd, const float* __restrict__ x, int d, int lane) {

@@ -196,7 +196,8 @@ int b2k_group_create(const int32_t* devices, int32_t n_devices, b2k_group** out)
     set_error("group_create: no CUDA device (this engine has no CPU path)");
     return B2K_E_NODEVICE;
   }
-  if (n_devices < 1 || n_devices > 16 || n_devices > ndev) { set_error("group_create: %d devices requested, %d visible", n_devices, ndev); return B2K_E_INVALID; }
+  // (a device may appear twice: two ranks on one GPU, as the single-GPU tests do; devices == NULL means 0 .. n-1)
+  if (n_devices < 1 || n_devices > 16 || (!devices && n_devices > ndev)) { set_error("group_create: %d devices requested, %d visible", n_devices, ndev); return B2K_E_INVALID; }
   b2k_group* g = new (std::nothrow) b2k_group();
   if (!g) { set_error("group_create: out of host memory"); return B2K_E_NOMEM; }
   g->n = n_devices;

@@ -245,4 +245,14 @@ ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, 
 int score_tc2_encode_db_map(void* tmap_db_out, const uint16_t* db_bf16, int64_t n_rows, int Dp);
 int launch_score_tc2(const ScoreTcArgs& a, cudaStream_t st);
 
+// Transposed CTA-pair variant (score_tn.cu): DB rows on M, up to 256 queries on N (tensor work proportional to
+// ceil(nq/16)*16; thread = DB row in the epilogue).  plan.n_splits = sub-splits (= partial lists), tiles of
+// score_tn_tile_rows() rows.  Needs tmap_db with 128-row boxes (score_tc2_encode_db_map) and its own query map.
+bool score_tn_supports(int Dp, int nq);
+int score_tn_tile_rows();
+int score_tn_n16(int nq);
+ScoreTcPlan score_tn_plan(int nq, int64_t n_rows, int n_sm);
+int score_tn_encode_q_map(void* tmap_q_out, const uint16_t* q_bf16, int nq_pad, int Dp, int nq);
+int launch_score_tn(const ScoreTcArgs& a, cudaStream_t st);
+
 }  // namespace b2k

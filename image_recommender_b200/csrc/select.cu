@@ -48,7 +48,8 @@ select_kernel(SelectArgs a, int P) {
   const int tid = threadIdx.x;
   if (tid < 4) s_ints[tid] = 0;
   if (a.k <= kList) {
-    select_small_k(a, q, skey, wtop, top, s_exact32, s_ints);     // first barrier inside: after the key load
+    if (a.n_lists <= kSelRegLists) select_small_k_reg(a, q, wtop, top, s_exact32, s_ints);
+    else select_small_k(a, q, skey, wtop, top, s_exact32, s_ints);     // first barrier inside: after the key load
     return;
   }
   load_list_keys(lst, E, skey);
@@ -125,7 +126,8 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
   int state = 0;
   if (rank == 0) {
     if (tid < 4) s_ints[tid] = 0;
-    const int flag = select_small_k(t.se, q, skey, wtop, top, s_exact32, s_ints);
+    const int flag = t.se.n_lists <= kSelRegLists ? select_small_k_reg(t.se, q, wtop, top, s_exact32, s_ints)
+                                                  : select_small_k(t.se, q, skey, wtop, top, s_exact32, s_ints);
     state = flag != 0 ? 2 : (s_ints[2] > 0 ? 1 : 0);
     if (tid == 0) {
       t.state[q] = state;
@@ -143,7 +145,9 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
     if (rank != 0) state = __ldcg(t.state + q);
   }
   if (state != 0) return;                     // uniform over the cluster
-  const int cnt = min(__ldcg(t.rr.cand_count + q), t.rr.cand_cap);
+  // rank 0 knows the count from its own shared memory (its global copy is written by ONE thread and is only
+  // ordered for the other CTAs, by the cluster barrier: reading it back here raced with that store)
+  const int cnt = rank == 0 ? min(s_ints[0], t.rr.cand_cap) : min(__ldcg(t.rr.cand_count + q), t.rr.cand_cap);
   double* qd = nullptr;
   if (q_smem) {
     qd = reinterpret_cast<double*>(skey + key_slots);
@@ -340,7 +344,7 @@ int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st) {
   // small batches: up to 8 CTAs share one query's row gathers; large ones: one CTA per query, the query widened
   // to fp64 in shared memory (halves the conversions of a throughput-bound re-rank, as in rerank_kernel)
   int csize = 1;
-  while (csize < 8 && nq * csize * 2 <= 4 * n_sm) csize *= 2;
+  while (csize < 16 && nq * csize * 2 <= 4 * n_sm) csize *= 2;       // 16: non-portable cluster size, opted in below
   const size_t q_bytes = (size_t)a.rr.D * sizeof(double);
   const int q_smem = csize == 1 && nq >= 8 * n_sm && (a.rr.D & 3) == 0 && q_bytes <= 64 * 1024 &&
                      ((reinterpret_cast<uintptr_t>(a.rr.db_f32) | reinterpret_cast<uintptr_t>(a.rr.q)) & 15) == 0;
@@ -348,6 +352,10 @@ int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st) {
   if (smem > 200 * 1024) { set_error("tail: %d key slots do not fit shared memory", key_slots); return B2K_E_INVALID; }
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (csize > 8) {
+    static bool np_ok = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!np_ok) { cudaGetLastError(); csize = 8; }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nq * csize), 1, 1);
   cfg.blockDim = dim3(kSelThreads, 1, 1);

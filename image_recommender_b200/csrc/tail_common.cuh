@@ -170,17 +170,136 @@ static __device__ __forceinline__ int select_small_k(const SelectArgs& a, int q,
   return flag;
 }
 
+// Register-resident form of select_small_k for n_lists <= kSelRegLists (the usual 148 or fewer): thread t holds
+// entries t, t + 256, ... — exactly the (warp = list mod 8, lane = entry) layout the candidate emission walks —
+// so the lists are fetched from L2 once, all loads in flight together, and neither the k-th-best search nor the
+// emission touches shared memory for them (batch 1, r1 phase timers: 6 us list load + 11 us top-k + 3 us
+// emission with the shared-memory form).  Same results bit for bit.
+constexpr int kSelRegPer = 20;
+constexpr int kSelRegLists = kSelRegPer * kSelThreads / kList;          // 160
+
+static __device__ __forceinline__ int select_small_k_reg(const SelectArgs& a, int q, uint64_t* wtop, uint64_t* top,
+                                                         float* s_exact32, int* s_ints) {
+  const int E = a.n_lists * kList;
+  const Cand* lst = a.partial + (int64_t)q * a.list_stride * kList;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* out_rows = a.cand_rows + (int64_t)q * a.cand_cap;
+  Cand cs[kSelRegPer];
+#pragma unroll
+  for (int i = 0; i < kSelRegPer; ++i) {
+    const int e = tid + i * kSelThreads;
+    Cand c; c.score = 0.f; c.row = -1;
+    if (e < E) {      // 8-byte L2 load: the lists were just written by the scoring kernel's other SMs
+      const long long raw = __ldcg(reinterpret_cast<const long long*>(lst + e));
+      c.score = __int_as_float((int)(raw & 0xffffffffll));
+      c.row = (int32_t)(raw >> 32);
+    }
+    cs[i] = c;
+  }
+  uint64_t key[kSelRegPer];
+#pragma unroll
+  for (int i = 0; i < kSelRegPer; ++i) {
+    const int e = tid + i * kSelThreads;
+    const uint32_t fk = cs[i].row < 0 ? 0u : float_key(cs[i].score);     // NaN scores -> 0: dropped
+    key[i] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - e)) : 0ull;
+  }
+  // k best of this warp's share, then warp 0 merges the 8 x k survivors (as block_topk_u64)
+  uint64_t prev = ~0ull;
+  for (int j = 0; j < a.k; ++j) {
+    uint64_t m = 0ull;
+#pragma unroll
+    for (int i = 0; i < kSelRegPer; ++i) if (key[i] < prev && key[i] > m) m = key[i];
+    m = warp_max_u64(m);
+    if (lane == 0) wtop[warp * 32 + j] = m;
+    prev = m;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = kSelThreads >> 5;
+    uint64_t prev2 = ~0ull;
+    for (int j = 0; j < a.k; ++j) {
+      uint64_t m = 0ull;
+      for (int e = lane; e < nw * a.k; e += 32) {
+        const uint64_t v = wtop[(e / a.k) * 32 + (e % a.k)];
+        if (v < prev2 && v > m) m = v;
+      }
+      m = warp_max_u64(m);
+      if (lane == 0) top[j] = m;
+      prev2 = m;
+    }
+  }
+  __syncthreads();
+  const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
+  float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
+  float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
+  if (bk != 0u && a.db_f32 != nullptr) tighten_threshold(a, q, lst, E, top, s_exact32, thr, lb);
+  const uint32_t thr_key = float_key(thr);              // score >= thr  <=>  key >= thr_key
+#pragma unroll
+  for (int i = 0; i < kSelRegPer; ++i) {
+    const int l = warp + i * (kSelThreads >> 5);          // this warp's i-th list; lane = entry
+    if (l < a.n_lists) {
+      const uint32_t sk = (uint32_t)(key[i] >> 32);
+      const bool hit = sk != 0u && sk >= thr_key;
+      const unsigned hm = __ballot_sync(0xffffffffu, hit);
+      bool emit = hm != 0u;
+      if (hm == 0xffffffffu) {                            // saturated list: K-collect's (select_small_k explains)
+        if (lane == 0) {
+          const int slot = a.sat_pairs ? atomicAdd(a.sat_count, 1) : a.sat_cap;
+          if (slot < a.sat_cap) { a.sat_pairs[slot] = make_int2(q, l); atomicAdd(&s_ints[2], 1); }
+          else s_ints[1] = 1;
+        }
+        if (a.sat_pairs) emit = false;
+      }
+      if (emit) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_ints[0], __popc(hm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) {
+          const int pos = base + __popc(hm & ((1u << lane) - 1u));
+          if (pos < a.cand_cap) out_rows[pos] = cs[i].row;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  int cnt = s_ints[0];
+  int flag = 0;
+  if (s_ints[1]) flag |= 1;
+  if (cnt > a.cand_cap) { flag |= 2; cnt = a.cand_cap; }
+  if (a.force_exact) flag |= 4;
+  if (tid == 0) {
+    a.cand_count[q] = cnt;
+    a.flags[q] = flag;
+    a.thr[q] = thr;
+    a.lb[q] = lb;
+  }
+  return flag;
+}
+
 // K-rerank of one query by `n_warps` warps (this warp is number `warp_id` of them): exact score (Spec R) of
 // candidates warp_id, warp_id + n_warps, ...  qd: the query widened to fp64 in shared memory, or null.
 static __device__ __forceinline__ void rerank_query(const RerankArgs& a, int q, int cnt, int warp_id, int n_warps, int lane,
                                                     const double* qd) {
   const float* __restrict__ qv = a.q + (int64_t)q * a.D;
-  for (int c = warp_id; c < cnt; c += n_warps) {
-    const int32_t row = __ldcg(a.cand_rows + (int64_t)q * a.cand_cap + c);    // written by another CTA just before
-    const float* x = a.db_f32 + (int64_t)row * a.D;
-    const double p = qd ? lane_dot64_qd(qd, x, a.D, lane) : lane_dot64(qv, x, a.D, lane);
-    const float ip = (float)warp_sum_f64(p);
-    if (lane == 0) a.cand_ip[(int64_t)q * a.cand_cap + c] = ip;
+  const int32_t* rows = a.cand_rows + (int64_t)q * a.cand_cap;       // written by another CTA just before: L2 reads
+  float* out = a.cand_ip + (int64_t)q * a.cand_cap;
+  if (qd) {
+    for (int c = warp_id; c < cnt; c += n_warps) {
+      const float* x = a.db_f32 + (int64_t)__ldcg(rows + c) * a.D;
+      const float ip = (float)warp_sum_f64(lane_dot64_qd(qd, x, a.D, lane));
+      if (lane == 0) out[c] = ip;
+    }
+    return;
+  }
+  // latency-bound form: two candidates per warp step (candidates 2w, 2w+1, then + 2 n_warps, ...)
+  for (int c = 2 * warp_id; c < cnt; c += 2 * n_warps) {
+    const bool two = c + 1 < cnt;
+    const float* x0 = a.db_f32 + (int64_t)__ldcg(rows + c) * a.D;
+    const float* x1 = two ? a.db_f32 + (int64_t)__ldcg(rows + c + 1) * a.D : x0;
+    double p0, p1;
+    lane_dot64_x2(qv, x0, x1, a.D, lane, p0, p1);
+    const float i0 = (float)warp_sum_f64(p0), i1 = (float)warp_sum_f64(p1);
+    if (lane == 0) { out[c] = i0; if (two) out[c + 1] = i1; }
   }
 }
 

@@ -14,8 +14,17 @@ Exact search replaces the approximate indexes; M / efConstruction / efSearch / n
 accepted and ignored.  `index.table_dims = [48, 128, 1792]` (before the first add) tells the engine
 where the per-table parts of a concatenated row are, so that each part is L2-normalised; without it
 the whole row is treated as one table.  GPU-only: every call raises B2KError without a B200.
+
+Distances.  The engine stores L2-normalised parts and ranks by inner product, which equals the reference's
+METRIC_L2 ranking exactly when all rows share one norm (the extractors emit unit-norm parts).
+Without `table_dims` the whole row is normalised: rows of norm sqrt(T) come back with distances 2 - 2cos
+instead of 1 + T - 2ip (same order, another scale; a warning says so once).  Rows whose norms DIFFER would be
+ranked differently from an L2 search over the raw rows: `add` refuses them (ValueError) unless
+`index.allow_renormalize = True` — silently altering the ranking is not an option.
 """
 from __future__ import annotations
+
+import logging
 
 import numpy as np
 
@@ -34,6 +43,8 @@ class _ExactIndex:
         self.table_dims = None
         self.hnsw = _HnswParams()
         self.is_trained = True
+        self.allow_renormalize = False
+        self._warned_scale = False
         self._shard: FlatShard | None = None
 
     def _ensure(self, capacity: int) -> FlatShard:
@@ -53,6 +64,20 @@ class _ExactIndex:
 
     def add(self, x) -> None:
         x = np.ascontiguousarray(x, dtype=np.float32)
+        if not self.table_dims and x.shape[0]:
+            # whole-row normalisation: harmless for equal-norm rows (order kept, distances rescaled), a different
+            # ranking from the reference's L2 index otherwise
+            norms = np.sqrt(np.einsum("ij,ij->i", x, x, dtype=np.float64))
+            lo, hi = float(norms.min()), float(norms.max())
+            if hi > 0 and (hi - lo) > 1e-3 * hi and not self.allow_renormalize:
+                raise ValueError(
+                    f"faiss_shim: rows have norms {lo:.4g} .. {hi:.4g}; the engine would normalise them and rank by "
+                    "cosine, which differs from the reference's L2 search over the raw rows.  Set index.table_dims "
+                    "(per-table unit-norm parts) or index.allow_renormalize = True to accept cosine ranking.")
+            if abs(hi - 1.0) > 1e-3 and not self._warned_scale:
+                logging.warning("faiss_shim: rows of norm %.4g are stored normalised (no table_dims): returned distances "
+                                "are 2 - 2cos instead of the raw squared L2 (same order)", hi)
+                self._warned_scale = True
         self._ensure(max(x.shape[0], 1024)).add(x)
 
     def search(self, x, k: int):

@@ -53,13 +53,15 @@ typedef struct b2k_index b2k_index;
 #define B2K_OPT_INLINE_SEED  10  /* <= 128 queries: seeding folded into the scoring launch (grid barrier): 1 on (default) */
 #define B2K_OPT_FUSED_TAIL   11  /* k <= 32: select + re-rank + finalize as ONE launch (cluster of CTAs per query), K-collect and  */
                                  /* K-exact finish their queries themselves: 1 on (default), 0 = one launch per stage (as k > 32) */
+#define B2K_OPT_TN           12  /* transposed K-score kernel (queries on the MMA's N, <= 256 queries): -1 auto (129..240 queries; */
+                                 /* narrow rows at small batches on long shards), 0 never, 1 whenever it applies              */
 #define B2K_OPT_SEED          7  /* K-score threshold seeding: 1 auto (default), 0 off, N > 1 = a sampling pass of  */
                                  /* N tiles per split (forces the three-launch form, no in-kernel seeding)        */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs above 128 queries unless the last 256-query */
                                  /* tile would be half empty, up to 896 queries), 0 single CTA, 1 pairs          */
 
 typedef struct b2k_stats {
-  int32_t path;            /* last search: 1 = K-scan, 2 = K-score (1 CTA), 3 = K-score (CTA pairs) */
+  int32_t path;            /* last search: 1 = K-scan, 2 = K-score (1 CTA), 3 = K-score (CTA pairs), 4 = K-score transposed (CTA pairs, queries on N) */
   int32_t n_splits;        /* DB splits (partial lists) per query                            */
   int32_t cand_slots;      /* candidate slots per query (capacity; rows actually re-ranked: n_candidates) */
   int32_t n_uncertified;   /* queries whose certificate failed -> served by exact fp32 scan  */

@@ -1,5 +1,5 @@
-"""GPU experiment: K-pack under a power-capped SM clock — register-resident kernel vs the two-pass kernel
-(B2K_PACK_TWO_PASS=1 in the environment selects the old one).  A sustained GEMM phase drives the clocks down,
+"""GPU experiment: K-pack under a power-capped SM clock — bulk-copy kernel vs the two-pass kernel
+(B2K_PACK_NO_BULK=1 in the environment selects the latter).  A sustained GEMM phase drives the clocks down,
 then 56 pack launches are timed one by one."""
 import json, os, statistics, sys, time
 sys.path.insert(0, ".")
@@ -29,5 +29,5 @@ for phase in ("cool", "after 3 s of GEMM", "interleaved with GEMM"):
         times += [e0.elapsed_time(e1) for e0, e1 in evs]
     ms = statistics.median(times)
     by = n_pack * (4.0 * D + 4.0 * D + 2.0 * Dp + 4.0)
-    print(json.dumps({"kernel": "two-pass" if os.environ.get("B2K_PACK_TWO_PASS") else "register", "phase": phase, "median_ms": round(ms, 4),
+    print(json.dumps({"kernel": "two-pass (pack_rows_kernel)" if os.environ.get("B2K_PACK_NO_BULK") else "bulk (pack_rows_bulk_kernel)", "phase": phase, "median_ms": round(ms, 4),
                       "min_ms": round(min(times), 4), "max_ms": round(max(times), 4), "GBps": round(by / ms / 1e6, 1), "sm_mhz": clk}), flush=True)

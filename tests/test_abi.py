@@ -110,3 +110,15 @@ def test_c_client_end_to_end(tmp_path):
     for args in (["20000", "9", "10"], ["3000", "130", "5"], ["5000", "3", "40"]):
         r = subprocess.run([str(exe), *args], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr)
+
+
+def test_faiss_shim_refuses_rows_of_unequal_norm_without_table_dims():
+    """without table_dims the shim would normalise whole rows and rank by cosine — a different ranking
+    from the reference's L2 index when the row norms differ.  It refuses before touching the GPU."""
+    import image_recommender_b200.faiss_shim as faiss
+    index = faiss.IndexHNSWFlat(8, 32)
+    x = np.ones((4, 8), np.float32)
+    x[2] *= 3.0
+    with pytest.raises(ValueError, match="norms"):
+        index.add(x)
+    assert index.ntotal == 0

@@ -301,3 +301,38 @@ def test_image_recommender_device_all(gpu, tmp_path, monkeypatch):
         assert a == b and a[0][0].name == f"img_{i:04d}.jpg"
     one.close()
     many.close()
+
+
+@pytest.mark.parametrize("dims,n", [(DIMS, 20000), ([48], 40000), ([128], 30000)])
+def test_transposed_kernel_matches_oracle(gpu, dims, n):
+    """score_tn_kernel (DB rows on the MMA's M, queries on N; path 4) returns the oracle's bits for every batch
+    size it serves (N = 16 ... 256 columns), with and without a seeded floor, through K-collect on a
+    near-duplicate burst, and equals the M = queries kernels bit for bit."""
+    import image_recommender_b200 as irb
+    from image_recommender_b200 import _capi
+    tabs, _ = _mk(n, dims)
+    for t in tabs:
+        t[5000:5200] = t[4000] * (1.0 + 1e-4 * np.arange(200, dtype=np.float32)[:, None])
+    pk = oracle.pack(tabs)
+    ix = irb.FlatShard(dims, n, device=gpu)
+    ix.add_tables(tabs)
+    q = oracle.synth_queries(dims, 256, n, n_clusters=8)
+    q[3] = pk["f32"][5100] / np.sqrt(np.float32(len(dims)))
+    q = oracle.normalize_l2(q)
+    for nq, k in ((1, 10), (5, 32), (16, 10), (17, 5), (100, 10), (130, 10), (160, 10), (200, 1), (255, 10), (256, 10)):
+        w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q[:nq], k, pk["norm2"])
+        ix.set_option(_capi.OPT_TN, 0)
+        base = ix.search_ip(q[:nq], k)
+        assert ix.stats()["path"] in (2, 3)
+        for seed in (1, 0):
+            ix.set_option(_capi.OPT_TN, 1)
+            ix.set_option(_capi.OPT_SEED, seed)
+            got = ix.search_ip(q[:nq], k)
+            st = ix.stats()
+            assert st["path"] == 4, st
+            assert np.array_equal(got[1], w_lab), (nq, k, seed)
+            assert np.array_equal(got[2].view(np.uint32), w_ip.view(np.uint32))
+            assert np.array_equal(got[0].view(np.uint32), w_dist.view(np.uint32))
+            assert np.array_equal(got[1], base[1]) and np.array_equal(got[2].view(np.uint32), base[2].view(np.uint32))
+        ix.set_option(_capi.OPT_SEED, 1)
+    ix.close()
