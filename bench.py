@@ -474,21 +474,24 @@ def main():
     r0, r1 = shard_range(n_total, world, rank)
     n_local = r1 - r0
 
-    # ---- K-pack (build half) timed alone, FIRST: the GPU is idle and cool, nothing else is resident.  Every
-    # launch is timed by its own pair of CUDA events; the median of >= 50 launches is reported with the SM
-    # clock sampled meanwhile (an HBM-bound kernel must not depend on it).
-    pack = None
-    if rank == 0:
+    # ---- K-pack (build half) timed alone.  Every launch is timed by its own pair of CUDA events; the median of
+    # >= 50 launches is reported with the SM clock sampled meanwhile and, as a yardstick measured in the SAME
+    # phase, the bandwidth of a device-to-device copy (the memory system itself slows down under the power cap, so a
+    # fraction of the cool-chip copy peak would blame the kernel for the chip's state).  Run twice: FIRST, on an
+    # idle cool chip with nothing else resident, and again right after the headline phase (power-capped clocks).
+    def pack_leg(phase):
         n_pack, per_round, rounds = 131072, 8, 7
         n_pack = max(1024, min(n_pack, int(n_pack * 1968 / D)))
         scratch = irb.FlatShard(DIMS, n_pack * per_round, device=local_rank)
         tabs = [torch.randn((n_pack, d), device=dev, dtype=torch.float32) for d in DIMS]
+        src = torch.empty(n_pack * 2560, device=dev, dtype=torch.float32)
+        dst = torch.empty_like(src)
         for _ in range(3):
             scratch.add_tables_device(tabs)
         torch.cuda.synchronize()
         pack_sampler = ClockSampler(local_rank)
         pack_sampler.start()
-        times = []
+        times, copies = [], []
         for _ in range(rounds):
             scratch.reset()
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(per_round)]
@@ -496,20 +499,30 @@ def main():
                 e0.record()
                 scratch.add_tables_device(tabs)
                 e1.record()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            dst.copy_(src)
+            c1.record()
             torch.cuda.synchronize()
             times += [e0.elapsed_time(e1) for e0, e1 in evs]
+            copies.append(c0.elapsed_time(c1))
         pack_clocks = pack_sampler.stop()
         ms_pack = statistics.median(times)
+        copy_gbs = 2.0 * src.numel() * 4 / (statistics.median(copies) * 1e-3) / 1e9
         bytes_pack = n_pack * (4.0 * D + 4.0 * D + 2.0 * Dp + 4.0)       # read fp32, write fp32 + bf16 + norm
-        pack = {"bound": "hbm", "kernel": "pack_rows_kernel", "rows_per_launch": n_pack, "kernel_ms": ms_pack,
-                "launches_timed": len(times), "kernel_ms_min": min(times), "kernel_ms_max": max(times),
-                "achieved": bytes_pack / (ms_pack * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": bytes_pack / (ms_pack * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                "rows_per_s": n_pack / (ms_pack * 1e-3), "sm_mhz": pack_clocks["sm_mhz"],
-                "algorithmic_bytes_per_launch": bytes_pack}
+        ach = bytes_pack / (ms_pack * 1e-3) / 1e9
+        out = {"bound": "hbm", "kernel": "pack_rows_kernel", "phase": phase, "rows_per_launch": n_pack, "kernel_ms": ms_pack,
+               "launches_timed": len(times), "kernel_ms_min": min(times), "kernel_ms_max": max(times),
+               "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+               "copy_gbs_same_phase": copy_gbs, "frac_of_same_phase_copy": ach / copy_gbs,
+               "rows_per_s": n_pack / (ms_pack * 1e-3), "sm_mhz": pack_clocks["sm_mhz"],
+               "algorithmic_bytes_per_launch": bytes_pack}
         scratch.close()
-        del tabs, scratch
+        del tabs, scratch, src, dst
         torch.cuda.empty_cache()
+        return out
+
+    pack = pack_leg("idle chip, before anything else") if rank == 0 else None
 
     # ---- build the shard
     shard = irb.FlatShard(DIMS, n_local, device=local_rank, base_offset=r0)
@@ -603,6 +616,12 @@ def main():
     torch.cuda.synchronize()
     q_host = qd.cpu().pin_memory()
     e2e_s, h2d, d2h = time_e2e(q_host, args.steps, args.warmup)
+    pack_hot = None
+    if rank == 0 and n_local * (6.0 * D + 2.0 * Dp) < 160e9:      # needs ~17 GB next to the shard
+        try:
+            pack_hot = pack_leg("right after the headline phase (power-capped clocks)")
+        except Exception as e:
+            pack_hot = {"error": str(e)[:200]}
 
     flops = 2.0 * B * n_local * D
     tc_ach = flops / (score_ms * 1e-3) / 1e12
@@ -759,7 +778,7 @@ def main():
                       "launches_per_step": launches, "exchange": (args.exchange if world > 1 else None), "exchange_matches_nccl": exchange_check,
                       "nccl_path_ms": alt_ms, "build_rows_per_s": n_local / build_s,
                       "pack_gbs": n_local * (4.0 * D + 4.0 * D + 2.0 * Dp) / build_s / 1e9,
-                      "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "sweep": sweep,
+                      "host_cores": len(os.sched_getaffinity(0)), "roofline_pack": pack, "roofline_pack_hot": pack_hot, "sweep": sweep,
                       "library_gemm_same_shape": yard,
                       "hnsw_baseline": hnsw},
         }

@@ -5,18 +5,15 @@
 //   main/search_from_image.py:322 (faiss.normalize_L2)
 // HBM-bound, one warp per row, 16-byte accesses, fixed summation order (oracle/b2k_oracle.c
 // follows the same order bit for bit).
-#include <stdlib.h>
-#include <algorithm>
-
 #include "common.cuh"
 #include "kernels.h"
-#include "ptx.cuh"
 
 namespace b2k {
 
 // One warp per row.  For each table: s = Σx² (spec order), inv = 1/sqrtf(s) if s > 0,
 // y = x*inv -> fp32 row, bf16(y) -> bf16 row; also ||y||² and ||bf16(y)-y||² per row.
-static __device__ __forceinline__ void pack_rows_body(const PackArgs& a) {
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(PackArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= a.n) return;
@@ -91,119 +88,6 @@ static __device__ __forceinline__ void pack_rows_body(const PackArgs& a) {
       if (nb > __ldcg(a.stat_bits + 1)) atomicMax(a.stat_bits + 1, nb);
     }
   }
-}
-
-__global__ void __launch_bounds__(256)
-pack_rows_kernel(PackArgs a) { pack_rows_body(a); }
-
-// Bulk-copy form of the same arithmetic for rows made of whole, 16-byte aligned chunks (every d_t a multiple of 4).
-// pack_rows_kernel is bound by the latency of its own global loads (ncu: 77 % of the warp stalls are "long
-// scoreboard", 0.56 eligible warps per scheduler), so its bandwidth follows the SM clock: 0.90 of the copy peak at
-// 1.96 GHz, 0.73 at 1.31 GHz under a power cap (profiles/experiments/r02_exp_pack.log).  Here no warp ever waits
-// on a global load or store instruction: every warp owns two row slots in shared memory; lane 0 streams a row's
-// table parts in with cp.async.bulk (completion on the slot's mbarrier) one iteration ahead, the warp computes
-// the norms from shared memory (conflict-free 16-byte accesses), scales IN PLACE, writes the bf16 row next to it,
-// and lane 0 streams both rows out with cp.async.bulk (bulk groups).  Persistent: one CTA of 8 warps per SM,
-// ~16 rows (126 KB of reads) in flight per SM whatever the SM clock.  Bit-identical results: Spec S order.
-namespace {
-constexpr int kBulkWarps = 8;
-constexpr int kBulkSlots = 2;
-}  // namespace
-
-__global__ void __launch_bounds__(kBulkWarps * 32, 1)
-pack_rows_bulk_kernel(PackArgs a, int slot_bytes, int bf16_off) {
-  extern __shared__ __align__(128) unsigned char pk_smem[];
-  __shared__ uint64_t bars[kBulkWarps * kBulkSlots];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t g = (int64_t)blockIdx.x * kBulkWarps + warp, G = (int64_t)gridDim.x * kBulkWarps;
-  unsigned char* my = pk_smem + (size_t)warp * kBulkSlots * slot_bytes;
-  uint64_t* bar = bars + warp * kBulkSlots;
-  if (lane == 0) {
-    for (int s = 0; s < kBulkSlots; ++s) ptx::mbar_init(&bar[s], 1);
-    ptx::fence_mbar_init();
-  }
-  // the zero padding of the bf16 rows (columns D .. Dp) is written once: nothing ever overwrites it
-  for (int s = 0; s < kBulkSlots; ++s) {
-    uint16_t* ob = reinterpret_cast<uint16_t*>(my + (size_t)s * slot_bytes + bf16_off);
-    for (int i = a.D + lane; i < a.Dp; i += 32) ob[i] = 0;
-  }
-  __syncwarp();
-  const uint32_t row_bytes = (uint32_t)a.D * 4u;
-  auto load_row = [&](int64_t r, int s) {        // lane 0 only
-    float* dst = reinterpret_cast<float*>(my + (size_t)s * slot_bytes);
-    ptx::mbar_arrive_expect_tx(&bar[s], row_bytes);
-    for (int t = 0; t < a.n_tables; ++t)
-      ptx::bulk_g2s(dst + a.col_off[t], a.tables[t] + r * (int64_t)a.strides[t], (uint32_t)a.dims[t] * 4u, &bar[s]);
-  };
-  if (lane == 0) {
-    for (int s = 0; s < kBulkSlots; ++s)
-      if (g + s * G < a.n) load_row(g + s * G, s);
-  }
-  int it = 0;
-  for (int64_t r = g; r < a.n; r += G, ++it) {
-    const int s = it % kBulkSlots;
-    float* row = reinterpret_cast<float*>(my + (size_t)s * slot_bytes);
-    uint16_t* ob = reinterpret_cast<uint16_t*>(my + (size_t)s * slot_bytes + bf16_off);
-    ptx::mbar_wait(&bar[s], (uint32_t)(it / kBulkSlots) & 1u);
-    float n2 = 0.f, e2 = 0.f;
-    for (int t = 0; t < a.n_tables; ++t) {
-      const int n4 = a.dims[t] >> 2, off = a.col_off[t];
-      float4* x4 = reinterpret_cast<float4*>(row + off);
-      float inv = 1.0f;
-      if (a.normalize) {
-        float p = 0.f;
-        for (int c = lane; c < n4; c += 32) {
-          const float4 v = x4[c];
-          p = __fmaf_rn(v.x, v.x, p); p = __fmaf_rn(v.y, v.y, p);
-          p = __fmaf_rn(v.z, v.z, p); p = __fmaf_rn(v.w, v.w, p);
-        }
-        const float ss = warp_sum_f32(p);
-        if (ss > 0.f) inv = __fdiv_rn(1.0f, __fsqrt_rn(ss));
-      }
-      float p2 = 0.f, pe = 0.f;
-      for (int c = lane; c < n4; c += 32) {
-        float4 v = x4[c];
-        v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv);
-        v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
-        const uint16_t b0 = f32_to_bf16_bits(v.x), b1 = f32_to_bf16_bits(v.y);
-        const uint16_t b2 = f32_to_bf16_bits(v.z), b3 = f32_to_bf16_bits(v.w);
-        p2 = __fmaf_rn(v.x, v.x, p2); p2 = __fmaf_rn(v.y, v.y, p2);
-        p2 = __fmaf_rn(v.z, v.z, p2); p2 = __fmaf_rn(v.w, v.w, p2);
-        const float d0 = __fsub_rn(bf16_bits_to_f32(b0), v.x), d1 = __fsub_rn(bf16_bits_to_f32(b1), v.y);
-        const float d2 = __fsub_rn(bf16_bits_to_f32(b2), v.z), d3 = __fsub_rn(bf16_bits_to_f32(b3), v.w);
-        pe = __fmaf_rn(d0, d0, pe); pe = __fmaf_rn(d1, d1, pe);
-        pe = __fmaf_rn(d2, d2, pe); pe = __fmaf_rn(d3, d3, pe);
-        x4[c] = v;
-        uint2 pk;
-        pk.x = (uint32_t)b0 | ((uint32_t)b1 << 16);
-        pk.y = (uint32_t)b2 | ((uint32_t)b3 << 16);
-        *reinterpret_cast<uint2*>(ob + off + 4 * c) = pk;
-      }
-      n2 = __fadd_rn(n2, warp_sum_f32(p2));
-      e2 = __fadd_rn(e2, warp_sum_f32(pe));
-    }
-    // this warp's shared-memory writes -> visible to the async engine, then lane 0 streams the slot out
-    ptx::fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      const int64_t r_out = a.row0 + r;
-      if (a.out_f32) ptx::bulk_s2g(a.out_f32 + r_out * (int64_t)a.D, row, row_bytes);
-      if (a.out_bf16) ptx::bulk_s2g(a.out_bf16 + r_out * (int64_t)a.Dp, ob, (uint32_t)a.Dp * 2u);
-      ptx::bulk_commit();
-      if (a.out_norm2) a.out_norm2[r_out] = n2;
-      if (a.stat_bits) {      // see pack_rows_kernel
-        const unsigned int eb = __float_as_uint(e2), nb = __float_as_uint(n2);
-        if (eb > __ldcg(a.stat_bits + 0)) atomicMax(a.stat_bits + 0, eb);
-        if (nb > __ldcg(a.stat_bits + 1)) atomicMax(a.stat_bits + 1, nb);
-      }
-      // the slot is refilled with the row this warp handles kBulkSlots iterations from now, as soon as the
-      // engine has read the slot out (the other slot's row is already in flight meanwhile)
-      const int64_t nxt = r + (int64_t)kBulkSlots * G;
-      if (nxt < a.n) { ptx::bulk_wait_read0(); load_row(nxt, s); }
-    }
-    __syncwarp();
-  }
-  if (lane == 0) ptx::bulk_wait_all();          // shared memory must outlive the last stores' reads
 }
 
 // faiss.normalize_L2 semantics: x *= 1/sqrtf(Σx²) iff Σx² > 0 (spec order), in place.
@@ -369,32 +253,15 @@ synth_rows_kernel(SynthArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Two alternatives were built and measured in round 2 and lost to this kernel (profiles/experiments/r02_exp_pack.log,
+// 131072 combo rows per launch; cool chip at 1965 MHz / after 3 s of GEMM at ~1300 MHz under the power cap):
+//   this two-pass kernel (second pass hits L1)                      0.435 ms / 0.53 ms
+//   register-resident rows, every load issued up front (112 regs)   0.545 ms / 0.70 ms   (16 warps per SM)
+//   cp.async.bulk rows through shared memory, 16 warps x 1 slot     0.467 ms / 0.61 ms   (row arithmetic issue-bound)
+// A device-to-device copy of the same size runs at 6513 GB/s cool and 5995 GB/s in the capped phase: the memory
+// system itself slows under the cap, and this kernel sits at 0.91 / 0.81 of the copy measured in the same phase.
 int launch_pack(const PackArgs& a, cudaStream_t st) {
   if (a.n <= 0) return 0;
-  // bulk-copy form when every table part is made of whole, 16-byte aligned chunks and two row slots per warp fit
-  bool bulk = (a.D & 3) == 0;
-  for (int t = 0; t < a.n_tables && bulk; ++t)
-    bulk = (a.dims[t] & 3) == 0 && (a.col_off[t] & 3) == 0 && (a.strides[t] & 3) == 0 &&
-           (reinterpret_cast<uintptr_t>(a.tables[t]) & 15) == 0;
-  bulk = bulk && ((reinterpret_cast<uintptr_t>(a.out_f32) | reinterpret_cast<uintptr_t>(a.out_bf16)) & 15) == 0;
-  const int bf16_off = a.D * 4;
-  const int slot_bytes = (bf16_off + a.Dp * 2 + 127) & ~127;
-  const size_t smem = (size_t)kBulkWarps * kBulkSlots * slot_bytes;
-  static const bool no_bulk = getenv("B2K_PACK_NO_BULK") != nullptr;      // A/B switch for experiments
-  if (bulk && !no_bulk && smem <= 200 * 1024) {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      B2K_CUDA(cudaGetDevice(&dev));
-      B2K_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
-    B2K_CUDA(cudaFuncSetAttribute(pack_rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t want = (a.n + kBulkWarps - 1) / kBulkWarps;
-    const int grid = (int)std::min<int64_t>(want, n_sm);
-    pack_rows_bulk_kernel<<<grid, kBulkWarps * 32, smem, st>>>(a, slot_bytes, bf16_off);
-    B2K_CHECK_LAUNCH();
-    return 0;
-  }
   const int wpb = 8;
   const int64_t blocks = (a.n + wpb - 1) / wpb;
   pack_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(a);

@@ -74,17 +74,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
-// ---- 1-D bulk async copy shared -> global (bulk groups), and the proxy fence that orders a thread's generic
-// shared-memory writes before the async engine reads them
-__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // ---- TMA 2-D tiled load (UTMALDG) -------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -223,6 +212,44 @@ __device__ __forceinline__ void umma_commit_pair_a(uint32_t bar, uint16_t mask) 
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(bar), "h"(mask)
+      : "memory");
+}
+
+// One K-block of 64 bf16 (four K=16 MMAs, descriptors advancing by 32 bytes = +2) and the commit that frees its
+// shared-memory stage, as ONE asm statement: ptxas wraps every tcgen05 asm statement issued under `if (lane == 0)`
+// in its own ELECT / BRA.U.ANY "waterfall" (~6 SASS instructions each); one statement pays for it once per K-block
+// instead of five times.  The issuing warp is the bottleneck whenever an MMA is short (N <= 128: 64 tensor cycles
+// per instruction against ~100 issue cycles, profiles/r02_prof_tn_128_stalls.txt).
+__device__ __forceinline__ void umma_bf16_pair_kblock(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                      uint32_t accumulate_first, uint32_t empty_bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "add.s64 a, %1, 2;\n\tadd.s64 b, %2, 2;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, 1;\n\t"
+      "add.s64 a, %1, 4;\n\tadd.s64 b, %2, 4;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, 1;\n\t"
+      "add.s64 a, %1, 6;\n\tadd.s64 b, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, 1;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(empty_bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_kblock(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate_first, uint32_t empty_bar) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "add.s64 a, %1, 2;\n\tadd.s64 b, %2, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, 1;\n\t"
+      "add.s64 a, %1, 4;\n\tadd.s64 b, %2, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, 1;\n\t"
+      "add.s64 a, %1, 6;\n\tadd.s64 b, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, 1;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(empty_bar)
       : "memory");
 }
 

@@ -82,7 +82,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int it = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int32_t row0 = (int32_t)((tile_begin + t) * kBlockN);
@@ -116,16 +116,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int kb = 0; kb < n_kblocks; ++kb) {
         ptx::mbar_wait_a(full_u + s * 8, ph);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (ptx::elect_one()) {       // elect.sync: ptxas then issues the tcgen05 instructions without a per-instruction waterfall
           const uint64_t a_desc = desc0 + (uint64_t)(s * (kStageBytes >> 4));
           const uint64_t b_desc = a_desc + (uint64_t)(kABytes >> 4);
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 32 bytes (16 bf16) inside the swizzled row: +2 in 16-byte units
-            ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc,
-                           (kb | k) != 0 ? 1u : 0u);
-          }
-          ptx::umma_commit_a(empty_u + s * 8);                 // frees the smem stage when the MMAs retire
+          static_assert(kBlockK / kUmmaK == 4, "umma_bf16_kblock issues four K=16 MMAs");
+          // four MMAs (descriptors advance 32 bytes = +2 inside the swizzled row) + the commit that frees the stage,
+          // one asm statement (ptx.cuh)
+          ptx::umma_bf16_kblock(d_tmem, a_desc, b_desc, kIdesc, kb != 0 ? 1u : 0u, empty_u + s * 8);
           if (kb == n_kblocks - 1) ptx::umma_commit_a(tfull_u + acc * 8);   // accumulator complete
         }
         __syncwarp();

@@ -74,7 +74,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int it = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int32_t row0 = (int32_t)((tile_begin + t) * kBlockN) + (int32_t)rank * kBHalfRows;
@@ -109,14 +109,12 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int kb = 0; kb < n_kblocks; ++kb) {
           ptx::mbar_wait_a(full_u + s * 8, ph);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {       // elect.sync: ptxas then issues the tcgen05 instructions without a per-instruction waterfall
             const uint64_t a_desc = desc0 + (uint64_t)(s * (kStageBytes2 >> 4));
             const uint64_t b_desc = a_desc + (uint64_t)(kABytes2 >> 4);
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              ptx::umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc2,
-                                  (kb | k) != 0 ? 1u : 0u);
-            ptx::umma_commit_pair_a(empty_u + s * 8, 3);                        // stage free in both CTAs
+            static_assert(kBlockK / kUmmaK == 4, "umma_bf16_pair_kblock issues four K=16 MMAs");
+            // four MMAs + the commit that frees the stage in both CTAs, one asm statement (ptx.cuh)
+            ptx::umma_bf16_pair_kblock(d_tmem, a_desc, b_desc, kIdesc2, kb != 0 ? 1u : 0u, empty_u + s * 8, 3);
             if (kb == n_kblocks - 1) ptx::umma_commit_pair_a(tfull_u + acc * 8, 3);   // accumulators ready in both
           }
           __syncwarp();

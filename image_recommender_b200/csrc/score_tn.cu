@@ -154,7 +154,7 @@ score_tn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
@@ -191,14 +191,11 @@ score_tn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int kb = 0; kb < n_kblocks; ++kb) {
           ptx::mbar_wait_a(full_u + s * 8, ph);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             const uint64_t a_desc = desc0 + (uint64_t)(s * (L.stage_bytes >> 4));     // DB rows: the M operand
             const uint64_t b_desc = a_desc + (uint64_t)(kTnABytes >> 4);              // queries: the N operand
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              ptx::umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                  (kb | k) != 0 ? 1u : 0u);
-            ptx::umma_commit_pair_a(empty_u + s * 8, 3);
+            static_assert(kBlockK / kUmmaK == 4, "umma_bf16_pair_kblock issues four K=16 MMAs");
+            ptx::umma_bf16_pair_kblock(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u, empty_u + s * 8, 3);
             if (kb == n_kblocks - 1) ptx::umma_commit_pair_a(tfull_u + acc * 8, 3);
           }
           __syncwarp();

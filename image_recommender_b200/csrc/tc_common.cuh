@@ -233,15 +233,21 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// The first CTA that times out POISONS the barrier (top bit of the counter): CTAs that arrive later — the rest of
+// a grid that is trickling onto the SMs another kernel leaves free — see the bit and leave at once instead of
+// burning the timeout one after the other (26 ms for a 148-CTA grid before: tests/test_gpu_round2.py).
+constexpr unsigned int kGridBarrierPoison = 0x80000000u;
+__device__ __forceinline__ void grid_barrier_poison(unsigned int* ctr) { atomicOr(ctr, kGridBarrierPoison); }
 __device__ __forceinline__ uint32_t grid_barrier_arrive_wait(unsigned int* ctr, unsigned int n) {
   __threadfence();
-  atomicAdd(ctr, 1u);
+  if (atomicAdd(ctr, 1u) & kGridBarrierPoison) return 0u;
   const unsigned long long t0 = global_timer_ns();
   for (;;) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v & kGridBarrierPoison) return 0u;
     if (v >= n) return 1u;
-    if (global_timer_ns() - t0 > kGridBarrierTimeoutNs) return 0u;
+    if (global_timer_ns() - t0 > kGridBarrierTimeoutNs) { grid_barrier_poison(ctr); return 0u; }
     __nanosleep(40);
   }
 }
@@ -255,7 +261,10 @@ __device__ __forceinline__ void seed_exchange(int seed_k, const float* __restric
   if (qi < nq) list_store(s_addr, r_addr, partial + ((int64_t)qi * n_lists + split) * kList);
   __threadfence();
   ptx::named_bar_sync(2, 128);
-  if (et == 0) scratch[8] = grid_barrier_arrive_wait(grid_bar + 0, (unsigned)n_ctas);
+  if (et == 0) {
+    scratch[8] = grid_barrier_arrive_wait(grid_bar + 0, (unsigned)n_ctas);
+    if (scratch[8] == 0u) grid_barrier_poison(grid_bar + 1);      // nobody waits for this CTA at the second barrier
+  }
   ptx::named_bar_sync(2, 128);
   const bool lists_ready = scratch[8] != 0u;
   if (lists_ready) {
