@@ -103,9 +103,17 @@ int run_all(b2k_group* g, std::function<int(int)> job) {
   g->cv_go.notify_all();
   std::unique_lock<std::mutex> lk(g->mu);
   g->cv_done.wait(lk, [&] { return g->pending == 0; });
+  // every failing rank is named: the root's "peer did not publish" is usually the CONSEQUENCE of a peer's own error
+  std::string all;
+  int first = 0;
   for (int r = 0; r < g->n; ++r)
-    if (g->status[r]) { set_error("device %d: %s", g->dev[r].device, g->errs[r].c_str()); return g->status[r]; }
-  return 0;
+    if (g->status[r]) {
+      if (!first) first = g->status[r];
+      if (!all.empty()) all += "; ";
+      all += "device " + std::to_string(g->dev[r].device) + " (rank " + std::to_string(r) + "): " + g->errs[r];
+    }
+  if (first) set_error("%s", all.c_str());
+  return first;
 }
 
 #define G_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error("%s -> %s", #expr, cudaGetErrorString(e_)); return (int)e_; } } while (0)

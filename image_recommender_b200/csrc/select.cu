@@ -353,8 +353,12 @@ int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st) {
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (csize > 8) {
-    static bool np_ok = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    if (!np_ok) { cudaGetLastError(); csize = 8; }
+    // a function attribute belongs to the CURRENT device's context: set it on every launch (a process-wide
+    // "done" flag left the second GPU of a single-process group without it: invalid cluster size there)
+    if (cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      csize = 8;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nq * csize), 1, 1);
