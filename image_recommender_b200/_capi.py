@@ -16,7 +16,7 @@ B2K_MAX_K = 1024
 B2K_LIST = 32
 
 OPT_PATH, OPT_RERANK, OPT_FORCE_EXACT, OPT_SCAN_MAX_B, OPT_SPLITS, OPT_TC_PAIR, OPT_SEED, OPT_TIGHTEN, OPT_COLLECT, OPT_INLINE_SEED = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
-OPT_FUSED_TAIL, OPT_TN = 11, 12
+OPT_FUSED_TAIL, OPT_TN, OPT_SAMPLE_WAVE = 11, 12, 13
 PATH_AUTO, PATH_SCAN, PATH_TC = 0, 1, 2
 E_INVALID, E_CAPACITY, E_IO, E_NODEVICE, E_NOMEM, E_UNSUPPORTED, E_PEER = -1, -2, -3, -4, -5, -6, -7
 

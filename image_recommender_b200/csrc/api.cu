@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -113,6 +114,7 @@ struct b2k_index {
   alignas(64) CUtensorMap tmap_qn;                     // queries as the N operand of the transposed kernel
   const void* tmap_qn_ptr = nullptr; int tmap_qn_rows = 0, tmap_qn_n16 = 0;
   int opt_tn = -1;                                     // transposed kernel: -1 auto, 0 never, 1 whenever it applies
+  int opt_sample_wave = 1;                             // sampling pass on one wave of long strided CTAs (0: first tiles of every split)
   const void* tmap_q_ptr = nullptr; int tmap_q_rows = 0;
   const void* tmap_db_ptr = nullptr; int64_t tmap_db_rows = -1;
   int coresident[2] = {-1, -1};               // CTAs of score_tc / score_tc2 resident at once (occupancy query, lazily)
@@ -285,9 +287,14 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // tiny batches on short splits: one launch without a floor beats sampling + seeding + main pass
     // (a single live query per warp inserts without divergence; profiles/experiments/r01_exp_path.log)
     bool seed = ix->opt_seed && tiles_per_split >= 16 && (ix->opt_seed > 1 || nq > 4 || tiles_per_split >= 128);
-    // sample ~0.75 % of the shard whatever the split count: a smaller sample leaves the floor too low
-    // (more list insertions in the main pass), a larger one costs more than it saves
-    int sample_tiles = ix->opt_seed > 1 ? ix->opt_seed : (int)((tiles_per_split * 3 + 200) / 400);
+    // Sample size.  A sample of f x N rows costs f x N rows of scoring and leaves ~k / f rows per query above the
+    // floor (each a potential list insertion in the main pass), whatever N: the optimum is f ~ 1 / sqrt(N).
+    // 1.5 sqrt(tiles) tiles in total: 0.76 % of a 10 M-row shard (the measured optimum there), 2.1 % of a 1.25 M-row
+    // shard (batch 4096: 15.05 vs 16.05 ms with 0.76 %; profiles/experiments/r02_exp_sample.log).
+    const int64_t sample_total = std::max<int64_t>(1, std::min<int64_t>(
+        ix->opt_seed > 1 ? (int64_t)ix->opt_seed * ta.plan.n_splits : (int64_t)(1.5 * std::sqrt((double)tiles_total) + 0.5),
+        tiles_total / 8));
+    int sample_tiles = (int)((sample_total + ta.plan.n_splits - 1) / ta.plan.n_splits);
     sample_tiles = (int)std::max<int64_t>(1, std::min<int64_t>(sample_tiles, tiles_per_split / 8));
     // One query tile on the single-CTA kernel = one resident CTA per split: the sampling pass, the seed
     // kernel and the re-read of the sampled tiles fold into the main launch (in-kernel seeding).
@@ -315,11 +322,31 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
       seed = false;
     }
     if (seed) {
-      ta.max_tiles = sample_tiles;
-      rc = pair ? launch_score_tc2(ta, st) : launch_score_tc(ta, st);
+      // The sampling pass scores the same NUMBER of tiles whatever its grid.  With the main pass's grid (every
+      // split its first sample_tiles tiles) a 4096-query batch on 10 M rows is 4736 CTAs of 2 tiles each: 32 waves
+      // of CTA set-up (TMEM allocation, barrier init, cluster sync, pipeline fill) around 16 us of work — 4.1-6.6 ms
+      // per step in the launch list (profiles/r02_launches_raw.csv), 4 % of the step.  Instead: ONE wave of CTAs,
+      // n_sm / (query tiles x CTAs per tile) splits per query tile, each scoring its share of the sample as tiles
+      // spread evenly over its row range (tile_stride; contiguous runs of near-duplicate images do not dominate
+      // the sample).  Fewer, longer lists also mean fewer list insertions (32 ln(rows/32) per list).
+      ScoreTcArgs ts = ta;
+      ts.max_tiles = sample_tiles;
+      const int cpp = pair ? 2 : 1;
+      const int one_wave = std::max(1, ix->n_sm / (ta.plan.n_qtiles * cpp));
+      if (ix->opt_sample_wave && k <= kList && one_wave < ta.plan.n_splits) {
+        const int64_t total = sample_total;
+        const int64_t per_split = tiles_total / one_wave;              // the shortest split's tiles
+        const int64_t mine = std::min<int64_t>((total + one_wave - 1) / one_wave, per_split);
+        if (mine >= 1) {
+          ts.plan = pair ? score_tc2_plan(nq, ix->ntotal, ix->n_sm, one_wave, 0) : score_tc_plan(nq, ix->ntotal, ix->n_sm, one_wave, 0);
+          ts.max_tiles = (int32_t)mine;
+          ts.tile_stride = (int32_t)std::max<int64_t>(1, per_split / mine);
+        }
+      }
+      rc = pair ? launch_score_tc2(ts, st) : launch_score_tc(ts, st);
       if (rc) return rc;
       SeedArgs sd;
-      sd.partial = w.partial; sd.n_lists = ta.plan.n_splits; sd.list_stride = w.n_lists; sd.k = k;
+      sd.partial = w.partial; sd.n_lists = ts.plan.n_splits; sd.list_stride = w.n_lists; sd.k = k;
       sd.eps = w.eps_tc; sd.thr_floor = w.thr_floor;
       rc = launch_seed(sd, nq, st);
       if (rc) return rc;
@@ -906,6 +933,8 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
     case B2K_OPT_TN:
       if (value < -1 || value > 1) break;
       ix->opt_tn = (int)value; return 0;
+    case B2K_OPT_SAMPLE_WAVE:
+      ix->opt_sample_wave = value != 0; return 0;
     case B2K_OPT_SEED:
       if (value < 0 || value > 4096) break;
       ix->opt_seed = (int)value; return 0;

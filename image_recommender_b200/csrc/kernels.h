@@ -214,7 +214,8 @@ struct ScoreTcArgs {
   ScoreTcPlan plan;
   Cand* partial;        // [nq, n_lists, kList]; CTA (qtile, split) fills list `split`
   int32_t n_lists;
-  int32_t max_tiles;    // > 0: sampling pass, every split scores only its first max_tiles tiles
+  int32_t max_tiles;    // > 0: sampling pass, every split scores only max_tiles of its tiles:
+  int32_t tile_stride = 1;  //      tiles begin, begin + stride, ... (spread over the split; main pass: 1)
   const float* thr_floor;   // [nq] seeded admission floor (may be null)
   // in-kernel seeding (single-CTA kernel, one query tile, every CTA resident): inside their first tile the
   // CTAs exchange their lists through `partial`, CTA s computes query s's floor into seed_floor, and all

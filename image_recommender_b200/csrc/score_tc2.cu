@@ -31,7 +31,8 @@ constexpr uint32_t kIdesc2 = make_idesc(2 * kBlockM, kBlockN);   // M=256 across
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  int64_t n_rows, int32_t n_kblocks, int32_t nq, int32_t n_qtiles, int32_t n_splits,
-                 int32_t n_lists, int32_t max_tiles, const float* __restrict__ thr_floor, Cand* __restrict__ partial,
+                 int32_t n_lists, int32_t max_tiles, int32_t tile_stride, const float* __restrict__ thr_floor,
+                Cand* __restrict__ partial,
                  int32_t seed_k, const float* __restrict__ seed_eps, float* seed_floor, unsigned int* grid_bar) {
   extern __shared__ unsigned char smem_raw[];
   // identical carve-up in both CTAs: the MMA and the multicast commits address the peer by offset
@@ -77,7 +78,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (ptx::elect_one()) {
       int it = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int32_t row0 = (int32_t)((tile_begin + t) * kBlockN) + (int32_t)rank * kBHalfRows;
+        const int32_t row0 = (int32_t)((tile_begin + (int64_t)t * tile_stride) * kBlockN) + (int32_t)rank * kBHalfRows;
         for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
           const int s = it % kStages2;
           ptx::mbar_wait(&empty[s], ((it / kStages2) & 1) ^ 1);
@@ -138,7 +139,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const bool bulk_first = __all_sync(0xffffffffu, qi >= nq || floor == -INFINITY);
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
-      const int64_t row0 = (tile_begin + t) * kBlockN;
+      const int64_t row0 = (tile_begin + (int64_t)t * tile_stride) * kBlockN;
       const int valid = (int)min((int64_t)kBlockN, n_rows - row0);
       ptx::mbar_wait(&tfull[acc], (t >> 1) & 1);
       ptx::tc_fence_after();
@@ -228,7 +229,7 @@ int launch_score_tc2(const ScoreTcArgs& a, cudaStream_t st) {
   const CUtensorMap* mq = reinterpret_cast<const CUtensorMap*>(a.tmap_q);
   const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(a.tmap_db);
   score_tc2_kernel<<<a.plan.grid, kThreads, kSmemBytes2, st>>>(*mq, *md, a.n_rows, a.Dp / kBlockK, a.nq,
-                                                              a.plan.n_qtiles, a.plan.n_splits, a.n_lists, a.max_tiles, a.thr_floor,
+                                                              a.plan.n_qtiles, a.plan.n_splits, a.n_lists, a.max_tiles, a.max_tiles > 0 && a.tile_stride > 1 ? a.tile_stride : 1, a.thr_floor,
                                                               a.partial, a.seed_k, a.seed_eps, a.seed_floor, a.grid_bar);
   B2K_CHECK_LAUNCH();
   return 0;

@@ -55,6 +55,8 @@ typedef struct b2k_index b2k_index;
                                  /* K-exact finish their queries themselves: 1 on (default), 0 = one launch per stage (as k > 32) */
 #define B2K_OPT_TN           12  /* transposed K-score kernel (queries on the MMA's N, <= 256 queries): -1 auto (129..240 queries; */
                                  /* narrow rows at small batches on long shards), 0 never, 1 whenever it applies              */
+#define B2K_OPT_SAMPLE_WAVE  13  /* sampling pass of the seeding on ONE wave of long CTAs with strided tiles: 1 on (default), */
+                                 /* 0 = the main pass's grid, every split its first tiles                                      */
 #define B2K_OPT_SEED          7  /* K-score threshold seeding: 1 auto (default), 0 off, N > 1 = a sampling pass of  */
                                  /* N tiles per split (forces the three-launch form, no in-kernel seeding)        */
 #define B2K_OPT_TC_PAIR       6  /* K-score kernel: -1 auto (CTA pairs above 128 queries unless the last 256-query */
