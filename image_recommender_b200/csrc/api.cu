@@ -421,7 +421,7 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // is prep, score, tail, K-collect (no-op), K-exact (no-op): 5 launches, 7 with a separate sampling pass
     TailArgs tl;
     tl.se = se; tl.rr = rr; tl.fa = fa; tl.state = w.state; tl.sat_n = w.sat_n;
-    rc = launch_tail(tl, nq, ix->n_sm, st);
+    rc = launch_tail(tl, nq, ix->n_sm, st, ix->opt_fused_tail != 2);
     if (rc) return rc;
     ++launches;
     if (ix->opt_collect) {
@@ -929,7 +929,8 @@ int b2k_set_option(b2k_index* ix, int32_t key, int64_t value) {
     case B2K_OPT_INLINE_SEED:
       ix->opt_inline_seed = value != 0; return 0;
     case B2K_OPT_FUSED_TAIL:
-      ix->opt_fused_tail = value != 0; return 0;
+      if (value < 0 || value > 2) break;
+      ix->opt_fused_tail = (int)value; return 0;
     case B2K_OPT_TN:
       if (value < -1 || value > 1) break;
       ix->opt_tn = (int)value; return 0;

@@ -140,7 +140,7 @@ struct TailArgs {
   int32_t* state;       // [nq] 0 = finished by the tail kernel, 1 = deferred to K-collect, 2 = to K-exact
   int32_t* sat_n;       // [nq] saturated (query, list) pairs handed to K-collect
 };
-int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st);
+int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st, bool dense = true);   // dense: 3 CTAs / SM at large batches
 
 // K-collect's deferred finish: after the last (pair, sub-split) work item of a query the same CTA runs
 // K-rerank and K-finalize for it.

@@ -111,7 +111,12 @@ select_kernel(SelectArgs a, int P) {
 //   all ranks: K-rerank, warp (rank, w) takes candidates rank * 8 + w, + 8 C, ...
 //   rank 0   : K-finalize
 // Dynamic shared memory: max(n_lists * 32, cand_cap) u64 keys, then (q_smem) D doubles.
-__global__ void __launch_bounds__(kSelThreads)
+// kMinBlocks: 1 = the cluster form of small batches (latency: every register the compiler wants, 126);
+//             3 = one CTA per query at large batches, where the kernel is a throughput problem — gathers in
+//                 flight per SM — and 2 resident CTAs of 126 registers left the SMs 25 % occupied
+//                 (profiles/r02_prof_tail_b4096_*: long-scoreboard 47 %, DRAM 35 % of peak).
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kSelThreads, kMinBlocks)
 tail_kernel(TailArgs t, int key_slots, int q_smem) {
   extern __shared__ uint64_t skey[];
   __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
@@ -124,6 +129,7 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
   const int q = blockIdx.x / (int)csize;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int state = 0;
+  B2K_PHASE(0);
   if (rank == 0) {
     if (tid < 4) s_ints[tid] = 0;
     const int flag = t.se.n_lists <= kSelRegLists ? select_small_k_reg(t.se, q, wtop, top, s_exact32, s_ints)
@@ -138,12 +144,14 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
       }
     }
   }
+  B2K_PHASE(1);
   if (csize > 1) {
     // rank 0's candidate list / state -> the other CTAs of the cluster (release / acquire at cluster scope)
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (rank != 0) state = __ldcg(t.state + q);
   }
+  B2K_PHASE(2);
   if (state != 0) return;                     // uniform over the cluster
   // rank 0 knows the count from its own shared memory (its global copy is written by ONE thread and is only
   // ordered for the other CTAs, by the cluster barrier: reading it back here raced with that store)
@@ -156,6 +164,7 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
     __syncthreads();
   }
   rerank_query(t.rr, q, cnt, (int)rank * (kSelThreads >> 5) + warp, (int)csize * (kSelThreads >> 5), lane, qd);
+  B2K_PHASE(3);
   if (csize > 1) {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -163,7 +172,9 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
   } else {
     __syncthreads();
   }
+  B2K_PHASE(4);
   finalize_small_k(t.fa, q, cnt, skey, wtop, top);
+  B2K_PHASE(5);
 }
 
 // One CTA per query: admission floor for the full pass from the lists of the sampling pass.
@@ -338,7 +349,7 @@ int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
   return 0;
 }
 
-int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st) {
+int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st, bool dense) {
   const int E = a.se.n_lists * kList;
   const int key_slots = std::max(E, (int)a.fa.cand_cap);
   // small batches: up to 8 CTAs share one query's row gathers; large ones: one CTA per query, the query widened
@@ -350,12 +361,13 @@ int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st) {
                      ((reinterpret_cast<uintptr_t>(a.rr.db_f32) | reinterpret_cast<uintptr_t>(a.rr.q)) & 15) == 0;
   const size_t smem = (size_t)key_slots * sizeof(uint64_t) + (q_smem ? q_bytes : 0);
   if (smem > 200 * 1024) { set_error("tail: %d key slots do not fit shared memory", key_slots); return B2K_E_INVALID; }
+  void (*kern)(TailArgs, int, int) = (dense && csize == 1 && nq >= 4 * n_sm) ? tail_kernel<3> : tail_kernel<1>;
   if (smem > 48 * 1024)
-    B2K_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2K_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (csize > 8) {
     // a function attribute belongs to the CURRENT device's context: set it on every launch (a process-wide
     // "done" flag left the second GPU of a single-process group without it: invalid cluster size there)
-    if (cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
       cudaGetLastError();
       csize = 8;
     }
@@ -369,7 +381,7 @@ int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st) {
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = (unsigned)csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  B2K_CUDA(cudaLaunchKernelEx(&cfg, tail_kernel, a, key_slots, q_smem));
+  B2K_CUDA(cudaLaunchKernelEx(&cfg, kern, a, key_slots, q_smem));
   return 0;
 }
 

@@ -12,6 +12,10 @@ cases = [([48, 128, 1792], 10_000_000, (160, 256, 384, 512, 1024, 4096)), ([48, 
          ([1792], 1_000_000, (1000,))]
 if len(sys.argv) > 3 and sys.argv[3] == "short":
     cases = [([48, 128, 1792], 10_000_000, (512, 4096)), ([48, 128, 1792], 1_250_000, (4096,))]
+if len(sys.argv) > 3 and sys.argv[3] == "tail":
+    cases = [([48, 128, 1792], 1_250_000, (32, 128, 256, 512, 1024, 2048, 4096)), ([48, 128, 1792], 10_000_000, (128, 1024, 4096))]
+if len(sys.argv) > 3 and sys.argv[3] == "big":
+    cases = [([48, 128, 1792], 1_250_000, (512, 1024, 2048, 4096)), ([48, 128, 1792], 10_000_000, (1024, 4096))]
 if len(sys.argv) > 3 and sys.argv[3] == "shards":
     cases = [([48, 128, 1792], 5_000_000, (512, 4096)), ([48, 128, 1792], 2_500_000, (512, 4096)), ([48, 128, 1792], 1_250_000, (512, 4096))]
 for dims, rows, batches in cases:
@@ -22,6 +26,7 @@ for dims, rows, batches in cases:
         q = s.synth_queries_device(B, total_rows=rows)
         ms = {v: [] for v in VALS}
         sc = {v: [] for v in VALS}
+        tl = {v: [] for v in VALS}
         labs = {}
         rounds = 15 if B <= 1024 else 7
         for r in range(rounds + 1):
@@ -35,11 +40,12 @@ for dims, rows, batches in cases:
                 e1.record(); torch.cuda.synchronize()
                 st = s.stats()
                 if r:
-                    ms[v].append(e0.elapsed_time(e1) / 2); sc[v].append(st["score_ms"])
+                    ms[v].append(e0.elapsed_time(e1) / 2); sc[v].append(st["score_ms"]); tl[v].append(st["tail_ms"])
                 labs[v] = out[1].clone()
         print(json.dumps({"dims": dims, "rows": rows, "B": B, "opt": OPT, "path": st["path"], "launches": st["launches"],
                           "median_ms": {v: round(statistics.median(ms[v]), 3) for v in VALS},
                           "min_ms": {v: round(min(ms[v]), 3) for v in VALS},
                           "median_score_ms": {v: round(statistics.median(sc[v]), 3) for v in VALS},
+                          "median_tail_ms": {v: round(statistics.median(tl[v]), 3) for v in VALS},
                           "same": all(bool(torch.equal(labs[VALS[0]], labs[v])) for v in VALS)}), flush=True)
     s.close()
