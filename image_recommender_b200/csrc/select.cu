@@ -111,7 +111,7 @@ select_kernel(SelectArgs a, int P) {
 //   all ranks: K-rerank, warp (rank, w) takes candidates rank * 8 + w, + 8 C, ...
 //   rank 0   : K-finalize
 // Dynamic shared memory: max(n_lists * 32, cand_cap) u64 keys, then (q_smem) D doubles.
-// kMinBlocks: 1 = the cluster form of small batches (latency: every register the compiler wants, 126);
+// kMinBlocks: 2 = the cluster form of small batches (126 registers: the lists of the selection live in registers);
 //             3 = one CTA per query at large batches, where the kernel is a throughput problem — gathers in
 //                 flight per SM — and 2 resident CTAs of 126 registers left the SMs 25 % occupied
 //                 (profiles/r02_prof_tail_b4096_*: long-scoreboard 47 %, DRAM 35 % of peak).
@@ -361,7 +361,7 @@ int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st, bool dense
                      ((reinterpret_cast<uintptr_t>(a.rr.db_f32) | reinterpret_cast<uintptr_t>(a.rr.q)) & 15) == 0;
   const size_t smem = (size_t)key_slots * sizeof(uint64_t) + (q_smem ? q_bytes : 0);
   if (smem > 200 * 1024) { set_error("tail: %d key slots do not fit shared memory", key_slots); return B2K_E_INVALID; }
-  void (*kern)(TailArgs, int, int) = (dense && csize == 1 && nq >= 4 * n_sm) ? tail_kernel<3> : tail_kernel<1>;
+  void (*kern)(TailArgs, int, int) = (dense && csize == 1 && nq >= 4 * n_sm) ? tail_kernel<3> : tail_kernel<2>;
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (csize > 8) {
