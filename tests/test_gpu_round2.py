@@ -355,3 +355,38 @@ def test_transposed_kernel_matches_oracle(gpu, dims, n):
             assert np.array_equal(got[1], base[1]) and np.array_equal(got[2].view(np.uint32), base[2].view(np.uint32))
         ix.set_option(_capi.OPT_SEED, 1)
     ix.close()
+
+
+def test_sampling_pass_one_wave_equals_main_grid_and_unseeded(gpu):
+    """The seeding's sampling pass on its own grid (one wave of long CTAs over strided tiles, 1.5 sqrt(tiles) tiles)
+    against the main pass's grid (every split its first tiles) and against no seeding at all: any subset of rows
+    gives a valid floor, so ids and scores are bit-identical — on the single-CTA kernel (3 query tiles), the
+    CTA-pair kernel (3 and 4 query tiles) and the transposed kernel (160 queries); a forced sample size too."""
+    import torch
+    import image_recommender_b200 as irb
+    from image_recommender_b200 import _capi
+    n, k = 2_000_000, 10
+    ix = irb.FlatShard(DIMS, n, device=gpu)
+    ix.fill_synthetic(n, total_rows=n)
+    q = ix.synth_queries_device(1000, total_rows=n)
+    src = np.array([oracle.synth_query_source(0x5EED, i, n) for i in range(1000)])
+    for m, path in ((160, 4), (300, 2), (700, 3), (1000, 3)):
+        got = {}
+        for name, wave, seed, launches in (("wave", 1, 1, 7), ("main_grid", 0, 1, 7), ("forced_sample", 1, 3, 7),
+                                            ("unseeded", 1, 0, 5)):
+            if path == 4 and seed == 0:
+                continue                       # the transposed kernel only runs behind a seeded floor
+            ix.set_option(_capi.OPT_SAMPLE_WAVE, wave)
+            ix.set_option(_capi.OPT_SEED, seed)
+            dist, lab, ip = ix.search_device(q[:m].contiguous(), k)
+            torch.cuda.synchronize()
+            st = ix.stats()
+            assert st["launches"] == launches and st["path"] == path and st["n_uncertified"] == 0, (name, m, st)
+            got[name] = (lab.cpu().numpy(), ip.cpu().numpy(), dist.cpu().numpy())
+        assert np.array_equal(got["wave"][0][:, 0], src[:m])
+        assert (np.diff(got["wave"][2], axis=1) >= 0).all()
+        for name in got:
+            assert np.array_equal(got["wave"][0], got[name][0]), (name, m)
+            assert np.array_equal(got["wave"][1].view(np.uint32), got[name][1].view(np.uint32)), (name, m)
+    ix.set_option(_capi.OPT_SAMPLE_WAVE, 1); ix.set_option(_capi.OPT_SEED, 1)
+    ix.close()
