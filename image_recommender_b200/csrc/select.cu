@@ -15,21 +15,21 @@
 //   merge    : cross-shard merge of per-GPU top-k lists.
 #include <algorithm>
 
-#include "tail_common.cuh"
-
-namespace b2k {
-
 #ifdef B2K_PHASE_TIMERS
 // debug build only (scripts/exp_phase.py): %globaltimer at the phase boundaries of select_kernel, CTA 0
-__device__ unsigned long long g_phase_t[16];
+namespace b2k { __device__ unsigned long long g_phase_t[16]; }
 #define B2K_PHASE(i) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; \
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_phase_t[i] = t_; } } while (0)
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); b2k::g_phase_t[i] = t_; } } while (0)
 extern "C" int b2k_debug_phase_times(unsigned long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_phase_t, sizeof(g_phase_t));
+  return (int)cudaMemcpyFromSymbol(out, b2k::g_phase_t, sizeof(b2k::g_phase_t));
 }
 #else
 #define B2K_PHASE(i) do { } while (0)
 #endif
+#include "tail_common.cuh"
+
+namespace b2k {
+
 
 // One CTA per query.  Dynamic smem: k <= 32: n_lists*32 u64 keys; k > 32: P u64 keys (P = the power of
 // two >= n_lists*32, sorted in place) + n_lists ints + k floats.

@@ -5,6 +5,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef B2K_PHASE
+#define B2K_PHASE(i) do { } while (0)      // debug build of select.cu only: phase stamps (scripts/exp_phase.py)
+#endif
+
 namespace b2k {
 
 namespace {
@@ -203,6 +207,7 @@ static __device__ __forceinline__ int select_small_k_reg(const SelectArgs& a, in
     const uint32_t fk = cs[i].row < 0 ? 0u : float_key(cs[i].score);     // NaN scores -> 0: dropped
     key[i] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - e)) : 0ull;
   }
+  B2K_PHASE(6);
   // k best of this warp's share, then warp 0 merges the 8 x k survivors (as block_topk_u64)
   uint64_t prev = ~0ull;
   for (int j = 0; j < a.k; ++j) {
@@ -232,7 +237,9 @@ static __device__ __forceinline__ int select_small_k_reg(const SelectArgs& a, in
   const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
   float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
   float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
+  B2K_PHASE(7);
   if (bk != 0u && a.db_f32 != nullptr) tighten_threshold(a, q, lst, E, top, s_exact32, thr, lb);
+  B2K_PHASE(8);
   const uint32_t thr_key = float_key(thr);              // score >= thr  <=>  key >= thr_key
 #pragma unroll
   for (int i = 0; i < kSelRegPer; ++i) {

@@ -9,7 +9,7 @@ lib = _capi.load_library()
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_250_000
 s = irb.FlatShard([48, 128, 1792], rows, device=0)
 s.fill_synthetic(rows, total_rows=rows)
-for B in (1, 16, 128):
+for B in (1, 128, 4096):
     q = s.synth_queries_device(B, total_rows=rows)
     for _ in range(4):
         s.search_device(q, 10)
@@ -18,4 +18,5 @@ for B in (1, 16, 128):
         t = (C.c_uint64 * 16)()
         lib.b2k_debug_phase_times(t)
         print(B, [int(t[i + 1] - t[i]) for i in range(5)], "ns: select, cluster barrier, re-rank, cluster barrier, finalize;",
+              [int(t[6] - t[0]), int(t[7] - t[6]), int(t[8] - t[7]), int(t[1] - t[8])], "ns inside select: list load, top-k, tighten, emit;",
               "tail_ms", round(st["tail_ms"], 4), "cands", st["n_candidates"])
