@@ -217,11 +217,15 @@ def cpu_baseline(rows: int, batch: int, k: int, n_total: int):
         cpu_flat.search_flat_ip(db, q, k)
         out[n] = time.perf_counter() - t0
     use_all_host_threads(cores)
-    t = out[cores]
-    return {"value": batch / t * (rows / n_total), "unit": UNIT, "cores": cores, "kind": "port",
+    # the CPU gets its best width: on SMT boxes OpenBLAS is faster on one thread per physical core than on all
+    # logical ones (8 of 16: 36.5 vs 30.5 QPS)
+    best = min(out, key=out.get)
+    t = out[best]
+    threads_used = best
+    return {"value": batch / t * (rows / n_total), "unit": UNIT, "cores": threads_used, "host_threads_available": cores, "kind": "port",
             "what": "exact-flat CPU port (faiss IndexFlatIP restated: OpenBLAS sgemm blocks 4096 x 1024 + OpenMP heaps), "
                     "extrapolated in rows",
-            "sample": f"{batch} queries x {rows} rows x D={D} fp32 in {t:.2f} s on {cores} threads; QPS scaled linearly "
+            "sample": f"{batch} queries x {rows} rows x D={D} fp32 in {t:.2f} s on {threads_used} threads (the fastest of the widths tried); QPS scaled linearly "
                       f"to {n_total} rows (x{n_total / rows:.1f})",
             "thread_scaling_qps": {str(n): batch / tt * (rows / n_total) for n, tt in out.items()}}
 

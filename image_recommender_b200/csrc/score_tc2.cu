@@ -187,7 +187,10 @@ ScoreTcPlan score_tc2_plan(int nq, int64_t n_rows, int n_sm, int forced_splits, 
     splits = forced_splits;
   } else {
     const int wave = n_sm / 2 > 0 ? n_sm / 2 : 1;
-    for (int div = 1; div <= 4; div <<= 1) {
+    // One query tile (129..256 queries): ONE wave of pairs, whatever the split length — the grid then seeds inside the
+    // launch (grid barrier among resident CTAs; no sampling pass, no seed kernel): 9.59 -> 9.31 ms at 256 queries on
+    // 10 M rows, 4.97 -> 4.59 ms on 5 M (profiles/experiments/r02_exp_splits74.log).
+    for (int div = p.n_qtiles == 1 ? 2 : 1; div <= 4; div <<= 1) {
       const int s = n_sm / div;
       if (s < 1 || s < min_splits || n_sm % div != 0 || ((int64_t)p.n_qtiles * s) % wave != 0) continue;
       splits = s;
