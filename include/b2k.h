@@ -52,7 +52,8 @@ typedef struct b2k_index b2k_index;
 #define B2K_OPT_COLLECT       9  /* saturated partial lists are re-scanned by K-collect: 1 on (default), 0 = exhaustive scan */
 #define B2K_OPT_INLINE_SEED  10  /* <= 128 queries: seeding folded into the scoring launch (grid barrier): 1 on (default) */
 #define B2K_OPT_FUSED_TAIL   11  /* k <= 32: select + re-rank + finalize as ONE launch (cluster of CTAs per query), K-collect and  */
-                                 /* K-exact finish their queries themselves: 1 on (default), 0 = one launch per stage (as k > 32) */
+                                 /* K-exact finish their queries themselves: 1 on (default), 0 = one launch per stage (as k > 32), */
+                                 /* 2 = on, without the 3-CTAs-per-SM instantiation for large batches (A/B measurements)          */
 #define B2K_OPT_TN           12  /* transposed K-score kernel (queries on the MMA's N, <= 256 queries): -1 auto (129..240 queries; */
                                  /* narrow rows at small batches on long shards), 0 never, 1 whenever it applies              */
 #define B2K_OPT_SAMPLE_WAVE  13  /* sampling pass of the seeding on ONE wave of long CTAs with strided tiles: 1 on (default), */
