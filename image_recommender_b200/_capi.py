@@ -84,6 +84,7 @@ SIGNATURES = {
     "b2k_xchg_destroy": (None, [C.c_void_p]),
     "b2k_xchg_handle": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2k_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2k_xchg_skip": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2k_xchg_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b2k_xchg_merge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2k_xchg_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),

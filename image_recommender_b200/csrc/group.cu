@@ -170,7 +170,16 @@ int run_search(b2k_group* g, int32_t nq, int32_t k) {
     const bool single = g->n == 1;
     int rc = b2k_search_device(d.shard, d.q, nq, k, single ? d.m_dist : d.dist, single ? d.m_lab : d.lab,
                                single ? d.m_ip : d.ip, d.stream);
-    if (rc) return rc;
+    if (rc) {
+      // the root must not wait 10 s for records that will never come: publish the epoch, keep this rank's error
+      if (!single && r != 0) {
+        const std::string keep = b2k_last_error();
+        b2k_xchg_skip(d.xchg, d.stream);
+        cudaStreamSynchronize(d.stream);
+        set_error("%s", keep.c_str());
+      }
+      return rc;
+    }
     if (!single) {
       rc = b2k_xchg_push(d.xchg, d.ip, d.dist, d.lab, nq, k, d.stream);
       if (rc) return rc;

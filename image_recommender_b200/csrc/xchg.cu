@@ -234,6 +234,21 @@ int b2k_xchg_push(b2k_xchg* x, const float* ip, const float* dist, const int64_t
   return 0;
 }
 
+int b2k_xchg_skip(b2k_xchg* x, void* stream) {
+  if (!x || !x->connected) { set_error("xchg_skip: bad argument or not connected"); return B2K_E_INVALID; }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  B2K_CUDA(cudaSetDevice(x->device));
+  x->epoch += 1;
+  const int parity = (int)(x->epoch & 1ull);
+  // n = 0: no records are stored; the single CTA publishes the epoch in every target's flag word
+  xchg_push_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x->peers, x->lay, x->rank, parity, x->epoch, nullptr, nullptr,
+                                                       nullptr, 0, x->done_ctas);
+  B2K_CHECK_LAUNCH();
+  if (prev >= 0) cudaSetDevice(prev);
+  return 0;
+}
+
 int b2k_xchg_merge(b2k_xchg* x, int32_t nq, int32_t k, float* out_ip, float* out_dist, int64_t* out_labels,
                    void* stream) {
   if (!x || !out_dist || !out_labels || nq < 1 || k < 1 || k > B2K_MAX_K || x->epoch == 0) {

@@ -208,6 +208,10 @@ int  b2k_xchg_merge(b2k_xchg* x, int32_t nq, int32_t k, float* out_ip, float* ou
  * resident index survives).  *timed_out_ranks: bit g = rank g was missing; returns B2K_E_PEER when non-zero
  * (the bits are cleared by the call). */
 int  b2k_xchg_status(b2k_xchg* x, uint32_t* timed_out_ranks);
+/* A rank whose local search FAILED still owes its peers an epoch: skip() publishes the next epoch without records
+ * (the peers' merges of this search return at once with stale entries for this rank; the caller is about to report
+ * the failure anyway) — otherwise every peer would wait out the 10 s timeout. */
+int  b2k_xchg_skip(b2k_xchg* x, void* stream);
 
 /* ---- several GPUs, ONE process ---------------------------------------------------------------------------
  * The reference's CLI / ImageRecommender is a single process (main/search_from_image.py:430-441): a b2k_group

@@ -390,3 +390,37 @@ def test_sampling_pass_one_wave_equals_main_grid_and_unseeded(gpu):
             assert np.array_equal(got["wave"][1].view(np.uint32), got[name][1].view(np.uint32)), (name, m)
     ix.set_option(_capi.OPT_SAMPLE_WAVE, 1); ix.set_option(_capi.OPT_SEED, 1)
     ix.close()
+
+
+def test_group_rank_failure_is_reported_at_once(gpu):
+    """A rank whose local search fails must not leave the root waiting out the exchange's 10 s peer timeout: it
+    publishes its epoch without records (b2k_xchg_skip) and the group call returns that rank's own error; the
+    next search, with the cause removed, is exact again."""
+    import image_recommender_b200 as irb
+    from image_recommender_b200 import _capi
+    from image_recommender_b200.sharded import shard_range
+    dims, n = [4160], 3000                                  # 4160 columns: beyond what K-scan supports
+    tabs = oracle.synth_rows(dims, n, total_rows=n, n_clusters=8)
+    pk = oracle.pack(tabs)
+    q = oracle.synth_queries(dims, 5, n, n_clusters=8)
+    devs = _group_devices()
+    grp = irb.ShardGroup(devs)
+    shards = []
+    for r, dev in enumerate(devs):
+        r0, r1 = shard_range(n, len(devs), r)
+        s = irb.FlatShard(dims, r1 - r0, device=dev, base_offset=r0)
+        s.add_tables([t[r0:r1] for t in tabs])
+        shards.append(s)
+    grp.set_shards(shards)
+    w_dist, w_lab, w_ip = oracle.search_exact(pk["f32"], q, 10, pk["norm2"])
+    assert np.array_equal(grp.search_ip(q, 10)[1], w_lab)
+    shards[1].set_option(_capi.OPT_PATH, _capi.PATH_SCAN)   # rank 1 alone: "no scoring path supports Dp"
+    t0 = time.perf_counter()
+    with pytest.raises(_capi.B2KError) as ei:
+        grp.search_ip(q, 10)
+    assert time.perf_counter() - t0 < 3.0, "the root waited for the peer timeout"
+    assert "rank 1" in str(ei.value) and "Dp" in str(ei.value), str(ei.value)
+    shards[1].set_option(_capi.OPT_PATH, _capi.PATH_AUTO)
+    got = grp.search_ip(q, 10)
+    assert np.array_equal(got[1], w_lab) and np.array_equal(got[2].view(np.uint32), w_ip.view(np.uint32))
+    grp.close()
