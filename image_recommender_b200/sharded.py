@@ -59,6 +59,12 @@ class PeerExchange:
         self._capi.check(self._lib.b2k_xchg_push(self._h, ip.data_ptr(), dist_t.data_ptr(), lab.data_ptr(), nq, k,
                                                  self._C.c_void_p(st)))
 
+    def skip(self, stream=None) -> None:
+        """Publish this rank's next epoch without records (its local search failed; the peers must not wait)."""
+        import torch
+        st = torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream if stream is None else stream
+        self._capi.check(self._lib.b2k_xchg_skip(self._h, self._C.c_void_p(st)))
+
     def merge(self, nq: int, k: int, out=None, stream=None):
         import torch
         dev = torch.device("cuda", self.device)
@@ -121,7 +127,13 @@ class ShardedSearcher:
         fl = send[m:].view(torch.float32)            # 2*m floats
         dist_t = fl[:m].view(nq, k)
         ip_t = fl[m:].view(nq, k)
-        self.local_search(q, k, (dist_t, lab, ip_t))
+        try:
+            self.local_search(q, k, (dist_t, lab, ip_t))
+        except Exception:
+            # this rank still owes its peers an epoch: without it every peer's merge waits out the 10 s timeout
+            if self.world > 1 and self.exchange is not None and nq * k <= self.exchange.max_entries:
+                self.exchange.skip()
+            raise
         if self.world == 1:
             return dist_t, lab, ip_t
         if self.exchange is not None and nq * k <= self.exchange.max_entries:
