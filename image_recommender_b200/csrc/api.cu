@@ -302,13 +302,16 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
     // Transposed kernel (score_tn.cu): tensor work proportional to the live queries and an epilogue thread per DB
     // row.  Auto (only while the kernel choice itself is on auto): (a) 129..208 queries, where the M = queries
     // kernels pay for 256 (steady state on 10 M rows: 130 queries 6.9 vs 7.9 ms, 160: 7.0 vs 8.0, 192: 7.8 vs 8.3,
-    // 224: equal; beyond, the pair kernel's M = 256 tile is full and its 4-deep ring of 32 KB stages wins);
+    // 224: equal; beyond, the pair kernel's M = 256 tile is full and its 4-deep ring of 32 KB stages wins) — on
+    // shards long enough that its two extra launches (sampling pass + seed kernel; the pair kernel seeds inside
+    // its launch) are noise: from 2.5 M rows up to 160 queries, from 4 M rows up to 208 (1.25 M rows: pair 1.01 vs
+    // 1.06 ms at 160 queries; 5 M rows: 4.27 vs 3.68; profiles/experiments/r02_exp_tn_short.log);
     // (b) narrow rows on long shards, where the 256-column drain per tile bounds the M = queries kernel: up to 48
     // queries at <= 64 columns (D = 48, 10 M rows: 0.66 vs 0.92 ms at 32 queries, 0.30 vs 0.32 at 1), 16..48 queries
     // at <= 128 columns (0.44 vs 0.53 ms).  Behind a seeded floor only.  profiles/experiments/r02_exp_tn.log.
     const bool tn_ok = k <= kList && score_tn_supports(ix->Dp, nq) && (ix->n_sm & ~1) <= w.n_lists && forced == 0;
     const bool tn_auto = seed && ix->opt_pair < 0 && ix->opt_path == 0 &&
-                         ((nq > 128 && nq <= 208) ||
+                         ((nq > 128 && nq <= 208 && ix->ntotal >= (nq <= 160 ? 2500000 : 4000000)) ||
                           (tiles_per_split >= 64 && nq <= 48 && (ix->Dp <= 64 || (ix->Dp <= 128 && nq >= 16))));
     const bool use_tn = tn_ok && (ix->opt_tn > 0 || (ix->opt_tn < 0 && tn_auto));
     // The grid barrier needs every CTA resident: the grid must fit what the occupancy query says this device

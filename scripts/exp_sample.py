@@ -18,6 +18,9 @@ if len(sys.argv) > 3 and sys.argv[3] == "big":
     cases = [([48, 128, 1792], 1_250_000, (512, 1024, 2048, 4096)), ([48, 128, 1792], 10_000_000, (1024, 4096))]
 if len(sys.argv) > 3 and sys.argv[3] == "mid":
     cases = [([48, 128, 1792], 10_000_000, (224, 240, 256)), ([48, 128, 1792], 5_000_000, (224, 256))]
+if len(sys.argv) > 3 and sys.argv[3] == "tnshort":
+    cases = [([48, 128, 1792], 1_250_000, (130, 160, 192, 208)), ([48, 128, 1792], 2_500_000, (130, 160, 192, 208)),
+             ([48, 128, 1792], 5_000_000, (130, 160, 192, 208))]
 if len(sys.argv) > 3 and sys.argv[3] == "shards":
     cases = [([48, 128, 1792], 5_000_000, (512, 4096)), ([48, 128, 1792], 2_500_000, (512, 4096)), ([48, 128, 1792], 1_250_000, (512, 4096))]
 for dims, rows, batches in cases:

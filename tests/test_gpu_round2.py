@@ -372,6 +372,7 @@ def test_sampling_pass_one_wave_equals_main_grid_and_unseeded(gpu):
     src = np.array([oracle.synth_query_source(0x5EED, i, n) for i in range(1000)])
     for m, path in ((160, 4), (300, 2), (700, 3), (1000, 3)):
         got = {}
+        ix.set_option(_capi.OPT_TN, 1 if path == 4 else -1)   # (auto takes the transposed kernel from 2.5 M rows on)
         for name, wave, seed, launches in (("wave", 1, 1, 7), ("main_grid", 0, 1, 7), ("forced_sample", 1, 3, 7),
                                             ("unseeded", 1, 0, 5)):
             if path == 4 and seed == 0:
@@ -388,7 +389,7 @@ def test_sampling_pass_one_wave_equals_main_grid_and_unseeded(gpu):
         for name in got:
             assert np.array_equal(got["wave"][0], got[name][0]), (name, m)
             assert np.array_equal(got["wave"][1].view(np.uint32), got[name][1].view(np.uint32)), (name, m)
-    ix.set_option(_capi.OPT_SAMPLE_WAVE, 1); ix.set_option(_capi.OPT_SEED, 1)
+    ix.set_option(_capi.OPT_SAMPLE_WAVE, 1); ix.set_option(_capi.OPT_SEED, 1); ix.set_option(_capi.OPT_TN, -1)
     ix.close()
 
 
