@@ -38,7 +38,7 @@ select_kernel(SelectArgs a, int P) {
   extern __shared__ uint64_t skey[];
   __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
   __shared__ uint64_t top[kList];
-  __shared__ float s_exact32[kList];
+  __shared__ __align__(8) float s_exact32[kList];
   __shared__ int s_ints[4];
   int& s_count = s_ints[0];
   int& s_sat = s_ints[1];
@@ -121,7 +121,7 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
   extern __shared__ uint64_t skey[];
   __shared__ uint64_t wtop[(kSelThreads / 32) * 32];
   __shared__ uint64_t top[kList];
-  __shared__ float s_exact32[kList];
+  __shared__ __align__(8) float s_exact32[kList];
   __shared__ int s_ints[4];
   unsigned int rank, csize;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));

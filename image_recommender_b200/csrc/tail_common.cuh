@@ -94,6 +94,8 @@ static __device__ __forceinline__ void tighten_threshold(const SelectArgs& a, in
                                                   const uint64_t* topk, float* s_exact, float& thr, float& lb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* qv = a.q + (int64_t)q * a.D;
+  // (gathering two rows per warp at once — lane_dot64_x2 — was measured: tighten 21 -> 16 us per CTA at batch 4096,
+  // but the extra live registers spill in the register-resident selection around it and give it all back)
   for (int j = warp; j < a.k; j += (kSelThreads >> 5)) {
     const int e = E - 1 - (int)(uint32_t)(topk[j] & 0xffffffffull);
     const float* x = a.db_f32 + (int64_t)lst[e].row * a.D;
@@ -208,32 +210,74 @@ static __device__ __forceinline__ int select_small_k_reg(const SelectArgs& a, in
     key[i] = fk ? (((uint64_t)fk << 32) | (uint32_t)(E - 1 - e)) : 0ull;
   }
   B2K_PHASE(6);
-  // k best of this warp's share, then warp 0 merges the 8 x k survivors (as block_topk_u64)
-  uint64_t prev = ~0ull;
-  for (int j = 0; j < a.k; ++j) {
-    uint64_t m = 0ull;
+  // The k best of the E keys, sorted, into top[0..k).  Two rank-counting passes over at most 256 keys each
+  // instead of k rounds of warp reductions over all of them (8.4 us of the batch-1 tail):
+  //   1. every thread's best key (the maximum of its <= 20 entries): 256 keys of DISJOINT entry sets, so their k-th
+  //      best L bounds the k-th best key overall from below;
+  //   2. every key >= L is collected (the k column maxima and the few other entries that beat L) and ranked.
+  // More than 256 keys at or above L (only with fewer than k non-empty columns, i.e. L = 0, and many entries): the
+  // k-round form below.
+  uint64_t* s_u64 = reinterpret_cast<uint64_t*>(s_exact32);       // [0] L, [1] collected count (free until tighten)
+  uint64_t cmax = 0ull;
 #pragma unroll
-    for (int i = 0; i < kSelRegPer; ++i) if (key[i] < prev && key[i] > m) m = key[i];
-    m = warp_max_u64(m);
-    if (lane == 0) wtop[warp * 32 + j] = m;
-    prev = m;
+  for (int i = 0; i < kSelRegPer; ++i) cmax = key[i] > cmax ? key[i] : cmax;
+  wtop[tid] = cmax;
+  if (tid == 0) { s_u64[0] = 0ull; s_u64[1] = 0ull; }
+  if (tid < kList) top[tid] = 0ull;
+  __syncthreads();
+  {
+    int rank = 0;
+    for (int e = 0; e < kSelThreads; ++e) { const uint64_t v = wtop[e]; rank += (v > cmax || (v == cmax && e < tid)) ? 1 : 0; }
+    if (rank == a.k - 1) s_u64[0] = cmax;                          // exactly one thread has this rank
   }
   __syncthreads();
-  if (warp == 0) {
-    const int nw = kSelThreads >> 5;
-    uint64_t prev2 = ~0ull;
-    for (int j = 0; j < a.k; ++j) {
-      uint64_t m = 0ull;
-      for (int e = lane; e < nw * a.k; e += 32) {
-        const uint64_t v = wtop[(e / a.k) * 32 + (e % a.k)];
-        if (v < prev2 && v > m) m = v;
-      }
-      m = warp_max_u64(m);
-      if (lane == 0) top[j] = m;
-      prev2 = m;
+  const uint64_t L = s_u64[0];
+  __syncthreads();                                                 // wtop is reused for the collected keys
+#pragma unroll
+  for (int i = 0; i < kSelRegPer; ++i)
+    if (key[i] != 0ull && key[i] >= L) {
+      const unsigned pos = atomicAdd(reinterpret_cast<unsigned int*>(s_u64 + 1), 1u);
+      if (pos < (unsigned)kSelThreads) wtop[pos] = key[i];
     }
-  }
   __syncthreads();
+  const int m = (int)(unsigned int)s_u64[1];
+  if (m <= kSelThreads) {
+    if (tid < m) {
+      const uint64_t mine = wtop[tid];
+      int rank = 0;
+      for (int e = 0; e < m; ++e) rank += wtop[e] > mine ? 1 : 0;  // keys are distinct (the slot is part of the key)
+      if (rank < a.k) top[rank] = mine;
+    }
+    __syncthreads();
+  } else {
+    __syncthreads();
+    // k best of this warp's share, then warp 0 merges the 8 x k survivors (as block_topk_u64)
+    uint64_t prev = ~0ull;
+    for (int j = 0; j < a.k; ++j) {
+      uint64_t mx = 0ull;
+#pragma unroll
+      for (int i = 0; i < kSelRegPer; ++i) if (key[i] < prev && key[i] > mx) mx = key[i];
+      mx = warp_max_u64(mx);
+      if (lane == 0) wtop[warp * 32 + j] = mx;
+      prev = mx;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int nw = kSelThreads >> 5;
+      uint64_t prev2 = ~0ull;
+      for (int j = 0; j < a.k; ++j) {
+        uint64_t mx = 0ull;
+        for (int e = lane; e < nw * a.k; e += 32) {
+          const uint64_t v = wtop[(e / a.k) * 32 + (e % a.k)];
+          if (v < prev2 && v > mx) mx = v;
+        }
+        mx = warp_max_u64(mx);
+        if (lane == 0) top[j] = mx;
+        prev2 = mx;
+      }
+    }
+    __syncthreads();
+  }
   const uint32_t bk = (uint32_t)(top[a.k - 1] >> 32);
   float thr = bk != 0u ? key_minus_2eps(bk, a.eps[q]) : -INFINITY;
   float lb = bk != 0u ? __fadd_rd(thr, a.eps[q]) : -INFINITY;
@@ -319,7 +363,20 @@ static __device__ __forceinline__ void finalize_small_k(const FinalizeArgs& a, i
   for (int c = tid; c < cnt; c += kSelThreads)
     fkeys[c] = cand_key(__ldcg(a.cand_ip + (int64_t)q * a.cand_cap + c), __ldcg(a.cand_rows + (int64_t)q * a.cand_cap + c));
   __syncthreads();
-  block_topk_u64(fkeys, cnt, a.k, wtop, top);
+  if (cnt <= kSelThreads) {
+    // few candidates (the usual case): every thread ranks its own key by counting the larger ones (keys are
+    // distinct: the row is part of the key) — one pass of broadcast shared-memory reads instead of 2 k rounds of
+    // warp reductions; the same k keys in the same order as block_topk_u64
+    const uint64_t mine = tid < cnt ? fkeys[tid] : 0ull;
+    int rank = 0;
+    for (int e = 0; e < cnt; ++e) { const uint64_t v = fkeys[e]; rank += (v > mine || (v == mine && e < tid)) ? 1 : 0; }
+    if (tid < kList) top[tid] = 0ull;
+    __syncthreads();
+    if (tid < cnt && mine != 0ull && rank < a.k) top[rank] = mine;
+    __syncthreads();
+  } else {
+    block_topk_u64(fkeys, cnt, a.k, wtop, top);
+  }
   for (int j = tid; j < a.k; j += kSelThreads) {
     const uint64_t best = top[j];
     float ip = -3.402823466e38f, dist = 3.402823466e38f;
