@@ -132,8 +132,10 @@ tail_kernel(TailArgs t, int key_slots, int q_smem) {
   B2K_PHASE(0);
   if (rank == 0) {
     if (tid < 4) s_ints[tid] = 0;
-    const int flag = t.se.n_lists <= kSelRegLists ? select_small_k_reg(t.se, q, wtop, top, s_exact32, s_ints)
-                                                  : select_small_k(t.se, q, skey, wtop, top, s_exact32, s_ints);
+    // (the dense instantiation keeps the lists in shared memory: with 80 registers the register-resident form spills)
+    const int flag = (kMinBlocks < 3 && t.se.n_lists <= kSelRegLists)
+                         ? select_small_k_reg(t.se, q, wtop, top, s_exact32, s_ints)
+                         : select_small_k(t.se, q, skey, wtop, top, s_exact32, s_ints);
     state = flag != 0 ? 2 : (s_ints[2] > 0 ? 1 : 0);
     if (tid == 0) {
       t.state[q] = state;
