@@ -112,9 +112,10 @@ select_kernel(SelectArgs a, int P) {
 //   rank 0   : K-finalize
 // Dynamic shared memory: max(n_lists * 32, cand_cap) u64 keys, then (q_smem) D doubles.
 // kMinBlocks: 2 = the cluster form of small batches (126 registers: the lists of the selection live in registers);
-//             3 = one CTA per query at large batches, where the kernel is a throughput problem — gathers in
+//         3, 4 = one CTA per query at large batches, where the kernel is a throughput problem — gathers in
 //                 flight per SM — and 2 resident CTAs of 126 registers left the SMs 25 % occupied
-//                 (profiles/r02_prof_tail_b4096_*: long-scoreboard 47 %, DRAM 35 % of peak).
+//                 (profiles/r02_prof_tail_b4096_*: long-scoreboard 47 %, DRAM 35 % of peak); 4 when the shared
+//                 memory of four CTAs fits (lists of <= 74 splits).
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kSelThreads, kMinBlocks)
 tail_kernel(TailArgs t, int key_slots, int q_smem) {
@@ -353,7 +354,9 @@ int launch_select(const SelectArgs& a, int nq, cudaStream_t st) {
 
 int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st, bool dense) {
   const int E = a.se.n_lists * kList;
-  const int key_slots = std::max(E, (int)a.fa.cand_cap);
+  // the tail kernel finalises only queries whose candidates all come from the lists (state 0: no K-collect rows):
+  // at most E of them, whatever the candidate capacity
+  const int key_slots = E;
   // small batches: up to 8 CTAs share one query's row gathers; large ones: one CTA per query, the query widened
   // to fp64 in shared memory (halves the conversions of a throughput-bound re-rank, as in rerank_kernel)
   int csize = 1;
@@ -363,7 +366,10 @@ int launch_tail(const TailArgs& a, int nq, int n_sm, cudaStream_t st, bool dense
                      ((reinterpret_cast<uintptr_t>(a.rr.db_f32) | reinterpret_cast<uintptr_t>(a.rr.q)) & 15) == 0;
   const size_t smem = (size_t)key_slots * sizeof(uint64_t) + (q_smem ? q_bytes : 0);
   if (smem > 200 * 1024) { set_error("tail: %d key slots do not fit shared memory", key_slots); return B2K_E_INVALID; }
-  void (*kern)(TailArgs, int, int) = (dense && csize == 1 && nq >= 4 * n_sm) ? tail_kernel<3> : tail_kernel<2>;
+  // large batches: as many resident CTAs per SM as shared memory allows (4 on shards with <= 74 lists, else 3)
+  const bool four = 4 * (smem + 4608) <= 227 * 1024;
+  void (*kern)(TailArgs, int, int) = !(dense && csize == 1 && nq >= 4 * n_sm) ? tail_kernel<2>
+                                     : four ? tail_kernel<4> : tail_kernel<3>;
   if (smem > 48 * 1024)
     B2K_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (csize > 8) {
