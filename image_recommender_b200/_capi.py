@@ -61,6 +61,9 @@ SIGNATURES = {
     "b2k_stage_close": (C.c_int, [C.c_void_p]),
     "b2k_ingest_sqlite": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64,
                                     C.POINTER(C.c_int64)]),
+    "b2k_ingest_sqlite_mt": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                       C.c_int64, C.POINTER(C.c_int64)]),
+    "b2k_stage_open_n": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
     "b2k_parse_f32_blob": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "b2k_table_dims": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "b2k_ntotal": (C.c_int64, [C.c_void_p]),

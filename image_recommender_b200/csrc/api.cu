@@ -32,6 +32,7 @@ namespace {
 constexpr int64_t kMaxStageRows = 65536;  // rows per staging chunk of add() / load() / fill_synthetic() (fewer for very wide rows)
 constexpr int kMaxNqPerPass = 16384;      // queries per pipeline pass (workspace sizing)
 constexpr int kDefaultCandCap = 0;      // 0: every listed entry can be a candidate (no overflow)
+constexpr int kMaxStageSlots = 32;     // pinned ingest staging slots (b2k_stage_open_n)
 constexpr int kCounterHead = 4;          // ints in front of the per-query counters of Workspace::fail_count
 constexpr int kEvRing = 64;             // pipeline passes whose device times b2k_get_stats can average
 
@@ -104,10 +105,12 @@ struct b2k_index {
   int64_t stage_rows = kMaxStageRows;         // rows per staging chunk: <= 512 MB of fp32 per chunk
   // pinned two-slot ingest staging (b2k_stage_*): host rows -> async H2D -> K-pack, overlapped with
   // the caller filling the other slot
-  float* pin[2][B2K_MAX_TABLES] = {{nullptr}};
+  float* pin[kMaxStageSlots][B2K_MAX_TABLES] = {{nullptr}};
+  unsigned char* pin_base = nullptr;          // the one pinned allocation behind pin[][]
   int64_t pin_rows = 0;
-  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
-  bool pin_busy[2] = {false, false};
+  int pin_slots = 0;                          // 2 (one decoding thread) .. kMaxStageSlots (two per ingest thread)
+  cudaEvent_t pin_ev[kMaxStageSlots] = {nullptr};
+  bool pin_busy[kMaxStageSlots] = {false};
   Workspace ws;
   // TMA descriptors (host copies; passed by value at launch)
   alignas(64) CUtensorMap tmap_q, tmap_db, tmap_db2;   // tmap_db2: 128-row boxes for the CTA-pair kernels
@@ -664,16 +667,28 @@ int b2k_add(b2k_index* ix, const float* const* host_tables, int64_t n) {
 }
 
 // ---- pinned two-slot ingest staging --------------------------------------------------------
-int b2k_stage_open(b2k_index* ix, int64_t rows_per_slot) {
-  if (!ix || rows_per_slot < 1) { set_error("stage_open: bad argument"); return B2K_E_INVALID; }
+int b2k_stage_open(b2k_index* ix, int64_t rows_per_slot) { return b2k_stage_open_n(ix, rows_per_slot, 2); }
+
+int b2k_stage_open_n(b2k_index* ix, int64_t rows_per_slot, int32_t n_slots) {
+  if (!ix || rows_per_slot < 1 || n_slots < 2 || n_slots > kMaxStageSlots) { set_error("stage_open: bad argument (2..%d slots)", kMaxStageSlots); return B2K_E_INVALID; }
   DeviceGuard g(ix->device);
   b2k_stage_close(ix);
   int rc = ensure_stage(ix);
   if (rc) return rc;
   rows_per_slot = std::min(rows_per_slot, ix->stage_rows);
-  for (int s = 0; s < 2; ++s) {
+  ix->pin_slots = n_slots;
+  // ONE pinned allocation for every slot and table (pinning and un-pinning cost per call and per page: 48 separate
+  // 32 MB buffers took 0.3 s to allocate and up to 1.4 s to free); each table part starts 256-byte aligned
+  size_t off = 0, part_off[B2K_MAX_TABLES];
+  for (int t = 0; t < ix->n_tables; ++t) {
+    part_off[t] = off;
+    off += ((size_t)rows_per_slot * ix->dims[t] * sizeof(float) + 255) & ~(size_t)255;
+  }
+  const size_t slot_bytes = off;
+  B2K_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ix->pin_base), slot_bytes * (size_t)n_slots));
+  for (int s = 0; s < n_slots; ++s) {
     for (int t = 0; t < ix->n_tables; ++t)
-      B2K_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ix->pin[s][t]), (size_t)rows_per_slot * ix->dims[t] * sizeof(float)));
+      ix->pin[s][t] = reinterpret_cast<float*>(ix->pin_base + (size_t)s * slot_bytes + part_off[t]);
     B2K_CUDA(cudaEventCreateWithFlags(&ix->pin_ev[s], cudaEventDisableTiming));
     ix->pin_busy[s] = false;
   }
@@ -684,7 +699,7 @@ int b2k_stage_open(b2k_index* ix, int64_t rows_per_slot) {
 int64_t b2k_stage_rows(const b2k_index* ix) { return ix ? ix->pin_rows : 0; }
 
 int b2k_stage_ptr(b2k_index* ix, int32_t slot, int32_t table, float** host_ptr) {
-  if (!ix || !host_ptr || slot < 0 || slot > 1 || table < 0 || table >= ix->n_tables || ix->pin_rows == 0) {
+  if (!ix || !host_ptr || slot < 0 || slot >= ix->pin_slots || table < 0 || table >= ix->n_tables || ix->pin_rows == 0) {
     set_error("stage_ptr: bad argument (stage open?)");
     return B2K_E_INVALID;
   }
@@ -693,7 +708,7 @@ int b2k_stage_ptr(b2k_index* ix, int32_t slot, int32_t table, float** host_ptr) 
 }
 
 int b2k_stage_wait(b2k_index* ix, int32_t slot) {
-  if (!ix || slot < 0 || slot > 1) { set_error("stage_wait: bad argument"); return B2K_E_INVALID; }
+  if (!ix || slot < 0 || slot >= ix->pin_slots) { set_error("stage_wait: bad argument"); return B2K_E_INVALID; }
   if (ix->pin_busy[slot]) {
     DeviceGuard g(ix->device);
     B2K_CUDA(cudaEventSynchronize(ix->pin_ev[slot]));
@@ -703,7 +718,7 @@ int b2k_stage_wait(b2k_index* ix, int32_t slot) {
 }
 
 int b2k_stage_commit(b2k_index* ix, int32_t slot, int64_t n) {
-  if (!ix || slot < 0 || slot > 1 || n < 0 || n > ix->pin_rows) { set_error("stage_commit: bad argument"); return B2K_E_INVALID; }
+  if (!ix || slot < 0 || slot >= ix->pin_slots || n < 0 || n > ix->pin_rows) { set_error("stage_commit: bad argument"); return B2K_E_INVALID; }
   if (ix->ntotal + n > ix->cap) {
     set_error("stage_commit: %lld + %lld rows exceed the capacity %lld", (long long)ix->ntotal, (long long)n, (long long)ix->cap);
     return B2K_E_CAPACITY;
@@ -729,12 +744,15 @@ int b2k_stage_close(b2k_index* ix) {
   if (!ix) return 0;
   DeviceGuard g(ix->device);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
-  for (int s = 0; s < 2; ++s) {
-    for (int t = 0; t < B2K_MAX_TABLES; ++t) { if (ix->pin[s][t]) cudaFreeHost(ix->pin[s][t]); ix->pin[s][t] = nullptr; }
+  for (int s = 0; s < kMaxStageSlots; ++s) {
+    for (int t = 0; t < B2K_MAX_TABLES; ++t) ix->pin[s][t] = nullptr;
     if (ix->pin_ev[s]) cudaEventDestroy(ix->pin_ev[s]);
     ix->pin_ev[s] = nullptr; ix->pin_busy[s] = false;
   }
+  if (ix->pin_base) cudaFreeHost(ix->pin_base);
+  ix->pin_base = nullptr;
   ix->pin_rows = 0;
+  ix->pin_slots = 0;
   return 0;
 }
 

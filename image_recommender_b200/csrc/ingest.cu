@@ -9,6 +9,12 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace b2k {
@@ -76,6 +82,8 @@ struct Sqlite {
   const void* (*column_blob)(void*, int) = nullptr;
   int (*column_bytes)(void*, int) = nullptr;
   const char* (*errmsg)(void*) = nullptr;
+  int (*bind_int64)(void*, int, long long) = nullptr;
+  int (*reset)(void*) = nullptr;
   bool load() {
     if (lib) return true;
     for (const char* name : {"libsqlite3.so.0", "libsqlite3.so"}) {
@@ -88,10 +96,12 @@ struct Sqlite {
     B2K_SYM(step, "sqlite3_step"); B2K_SYM(finalize, "sqlite3_finalize"); B2K_SYM(column_count, "sqlite3_column_count");
     B2K_SYM(column_type, "sqlite3_column_type"); B2K_SYM(column_int64, "sqlite3_column_int64");
     B2K_SYM(column_blob, "sqlite3_column_blob"); B2K_SYM(column_bytes, "sqlite3_column_bytes"); B2K_SYM(errmsg, "sqlite3_errmsg");
+    B2K_SYM(bind_int64, "sqlite3_bind_int64"); B2K_SYM(reset, "sqlite3_reset");
 #undef B2K_SYM
     return true;
   }
 };
+constexpr int kSqliteOpenNoMutex = 0x8000;
 constexpr int kSqliteOpenReadonly = 1, kSqliteRow = 100, kSqliteDone = 101, kSqliteInteger = 1, kSqliteBlob = 4;
 
 }  // namespace
@@ -182,6 +192,131 @@ int b2k_ingest_sqlite(b2k_index* ix, const char* db_path, const char* sql, int64
   const int rc2 = b2k_stage_wait(ix, 0) | b2k_stage_wait(ix, 1);
   *n_added = rc ? total - in_slot : total;
   return rc ? rc : rc2;
+}
+
+int b2k_ingest_sqlite_mt(b2k_index* ix, const char* db_path, const char* sql_range, const int64_t* id_bounds,
+                         int64_t n_chunks, int32_t n_threads, int64_t* ids_out, int64_t ids_cap, int64_t* n_added) {
+  if (!ix || !db_path || !sql_range || !id_bounds || !ids_out || !n_added || n_chunks < 0 || n_threads < 1) {
+    set_error("ingest_sqlite_mt: bad argument");
+    return B2K_E_INVALID;
+  }
+  *n_added = 0;
+  static Sqlite sq;
+  static std::mutex load_mu;
+  {
+    std::lock_guard<std::mutex> lk(load_mu);
+    if (!sq.load()) { set_error("ingest_sqlite: libsqlite3 is not loadable (%s)", dlerror()); return B2K_E_UNSUPPORTED; }
+  }
+  int32_t dims[B2K_MAX_TABLES];
+  const int n_tables = b2k_table_dims(ix, dims);
+  const int64_t slot_rows = b2k_stage_rows(ix);
+  if (slot_rows == 0) { set_error("ingest_sqlite_mt: b2k_stage_open_n(idx, rows, 2 * n_threads) first"); return B2K_E_INVALID; }
+  n_threads = (int32_t)std::max<int64_t>(1, std::min<int64_t>(n_threads, std::max<int64_t>(n_chunks, 1)));
+  {
+    float* probe = nullptr;                      // two slots per thread must exist
+    if (b2k_stage_ptr(ix, 2 * n_threads - 1, 0, &probe) != 0) { set_error("ingest_sqlite_mt: fewer than %d staging slots are open", 2 * n_threads); return B2K_E_INVALID; }
+  }
+
+  struct Shared {
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t turn = 0;            // next chunk to commit
+    int64_t total = 0;           // rows committed (== appended, in order)
+    int rc = 0;                  // first failure
+    std::string err;
+  } sh;
+
+  auto fail = [&](int rc, const std::string& msg) {
+    std::lock_guard<std::mutex> lk(sh.mu);
+    if (!sh.rc) { sh.rc = rc; sh.err = msg; }
+    sh.cv.notify_all();
+  };
+
+  auto worker = [&](int p) {
+    void* db = nullptr;
+    void* stmt = nullptr;
+    if (sq.open_v2(db_path, &db, kSqliteOpenReadonly | kSqliteOpenNoMutex, nullptr) != 0) {
+      fail(B2K_E_IO, std::string("ingest_sqlite: cannot open ") + db_path + ": " + (db ? sq.errmsg(db) : "out of memory"));
+      if (db) sq.close(db);
+      return;
+    }
+    if (sq.prepare_v2(db, sql_range, -1, &stmt, nullptr) != 0) {
+      fail(B2K_E_IO, std::string("ingest_sqlite: ") + sq.errmsg(db));
+      sq.close(db);
+      return;
+    }
+    if (sq.column_count(stmt) != 1 + n_tables) {
+      fail(B2K_E_INVALID, "ingest_sqlite: the query returns " + std::to_string(sq.column_count(stmt)) + " columns, expected id + " +
+                              std::to_string(n_tables) + " blobs");
+      sq.finalize(stmt); sq.close(db);
+      return;
+    }
+    std::vector<int64_t> ids((size_t)slot_rows);
+    float* dst[B2K_MAX_TABLES];
+    int64_t it = 0;
+    for (int64_t c = p; c < n_chunks; c += n_threads, ++it) {
+      { std::lock_guard<std::mutex> lk(sh.mu); if (sh.rc) break; }
+      const int slot = 2 * p + (int)(it & 1);
+      int rc = b2k_stage_wait(ix, slot);
+      for (int t = 0; t < n_tables && !rc; ++t) rc = b2k_stage_ptr(ix, slot, t, &dst[t]);
+      if (rc) { fail(rc, b2k_last_error()); break; }
+      sq.reset(stmt);
+      sq.bind_int64(stmt, 1, (long long)id_bounds[c]);
+      sq.bind_int64(stmt, 2, (long long)id_bounds[c + 1]);
+      int64_t n = 0;
+      std::string msg;
+      for (;;) {
+        const int st = sq.step(stmt);
+        if (st == kSqliteDone) break;
+        if (st != kSqliteRow) { rc = B2K_E_IO; msg = std::string("ingest_sqlite: ") + sq.errmsg(db); break; }
+        if (n >= slot_rows) { rc = B2K_E_INVALID; msg = "ingest_sqlite_mt: a chunk holds more than " + std::to_string(slot_rows) + " rows"; break; }
+        if (sq.column_type(stmt, 0) != kSqliteInteger) { rc = B2K_E_UNSUPPORTED; msg = "ingest_sqlite: first column is not an integer id"; break; }
+        const long long id = sq.column_int64(stmt, 0);
+        for (int t = 0; t < n_tables; ++t) {
+          const float* payload = nullptr;
+          int64_t d = 0;
+          const void* blob = sq.column_type(stmt, 1 + t) == kSqliteBlob ? sq.column_blob(stmt, 1 + t) : nullptr;
+          const int nb = blob ? sq.column_bytes(stmt, 1 + t) : 0;
+          if (parse_blob(static_cast<const unsigned char*>(blob), nb, &payload, &d) != 0 || d != dims[t]) {
+            rc = B2K_E_UNSUPPORTED;
+            msg = "ingest_sqlite: image id " + std::to_string(id) + ", table " + std::to_string(t) +
+                  ": blob is not a pickled 1-D float32 ndarray of " + std::to_string(dims[t]) + " values";
+            break;
+          }
+          memcpy(dst[t] + n * dims[t], payload, (size_t)d * sizeof(float));
+        }
+        if (rc) break;
+        ids[(size_t)n++] = id;
+      }
+      if (rc) { fail(rc, msg); break; }
+      // commit in chunk order: rows, offsets and ids_out are those of the single-threaded loop
+      std::unique_lock<std::mutex> lk(sh.mu);
+      sh.cv.wait(lk, [&] { return sh.turn == c || sh.rc != 0; });
+      if (sh.rc) break;
+      if (sh.total + n > ids_cap) {
+        sh.rc = B2K_E_CAPACITY; sh.err = "ingest_sqlite: more than " + std::to_string(ids_cap) + " rows";
+        sh.cv.notify_all();
+        break;
+      }
+      rc = b2k_stage_commit(ix, slot, n);
+      if (rc) { sh.rc = rc; sh.err = b2k_last_error(); sh.cv.notify_all(); break; }
+      memcpy(ids_out + sh.total, ids.data(), (size_t)n * sizeof(int64_t));
+      sh.total += n;
+      sh.turn = c + 1;
+      sh.cv.notify_all();
+    }
+    sq.finalize(stmt);
+    sq.close(db);
+  };
+
+  std::vector<std::thread> th;
+  for (int p = 0; p < n_threads; ++p) th.emplace_back(worker, p);
+  for (std::thread& t : th) t.join();
+  int rc2 = 0;
+  for (int s = 0; s < 2 * n_threads; ++s) rc2 |= b2k_stage_wait(ix, s);
+  *n_added = sh.total;
+  if (sh.rc) { set_error("%s", sh.err.c_str()); return sh.rc; }
+  return rc2;
 }
 
 }  // extern "C"

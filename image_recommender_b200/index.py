@@ -148,6 +148,25 @@ class FlatShard:
             _lib.b2k_stage_close(self._h)
         return ids[:n.value].copy()
 
+    def ingest_sqlite_mt(self, db_path: str, sql_range: str, id_bounds, max_rows: int, n_threads: int,
+                         rows_per_slot: int = 4096) -> np.ndarray:
+        """`ingest_sqlite` with `n_threads` reader threads (b2k_ingest_sqlite_mt): `sql_range` is the query with
+        `i.id >= ?1 AND i.id < ?2`, `id_bounds` cuts the ids into chunks of at most `rows_per_slot` images.  Every
+        thread has its own connection and two staging slots; chunks are committed in order, so rows, offsets and
+        the returned ids equal those of the single-threaded call."""
+        bounds = np.ascontiguousarray(id_bounds, dtype=np.int64)
+        n_chunks = int(bounds.size) - 1
+        n_threads = max(1, min(int(n_threads), 16, max(n_chunks, 1)))
+        ids = np.empty((max(int(max_rows), 1),), np.int64)
+        n = C.c_int64(0)
+        check(_lib.b2k_stage_open_n(self._h, int(rows_per_slot), 2 * n_threads))
+        try:
+            check(_lib.b2k_ingest_sqlite_mt(self._h, str(db_path).encode(), sql_range.encode(), bounds.ctypes.data,
+                                            n_chunks, n_threads, ids.ctypes.data, int(max_rows), C.byref(n)))
+        finally:
+            _lib.b2k_stage_close(self._h)
+        return ids[:n.value].copy()
+
     def search(self, q, k: int):
         """index.search(query_vec, k) (search_from_image.py:247) -> (distances, labels)."""
         dist, lab, _ = self.search_ip(q, k, want_ip=False)

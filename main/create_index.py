@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import argparse
 import logging
+import os
 import pickle
 import sqlite3
 import sys
@@ -41,6 +42,7 @@ class FAISSIndexBuilderDB:
         log_dir: str = "logs",
         device: int = 0,
         native_ingest: bool = True,
+        ingest_threads: int | None = None,
         sharded: bool = None,
     ):
         # reference: create_index.py:14-53 (same attribute names; `device` is new)
@@ -64,6 +66,7 @@ class FAISSIndexBuilderDB:
         self.efSearch = efSearch
         self.device = device
         self.native_ingest = native_ingest     # new: SQL -> decode -> pack loop in libb2k.so (csrc/ingest.cu)
+        self.ingest_threads = ingest_threads   # new: reader threads of the native ingest (None: half the cores, <= 8)
         # new: under torchrun (torch.distributed initialised, world > 1) every rank ingests and packs ITS row
         # range on its own GPU and all ranks write one index file together (None = auto, False = never)
         self.sharded = sharded
@@ -246,7 +249,16 @@ class FAISSIndexBuilderDB:
             return None, []
         index = self._initialize_index(dims, total)
         try:
-            ids = index.ingest_sqlite(self.db_path, sql, total)
+            threads = self._ingest_threads(total)
+            if threads > 1:
+                # several reader threads, each on its own connection over a range of image ids, committed in id
+                # order: the same rows, offsets and ids as the single-threaded loop
+                rows_per_slot = 2048
+                bounds = self._id_chunk_bounds(rows_per_slot)
+                sql_range = f"SELECT {select_cols} FROM images i {join_strs} WHERE i.id >= ?1 AND i.id < ?2 ORDER BY i.id"
+                ids = index.ingest_sqlite_mt(self.db_path, sql_range, bounds, total, threads, rows_per_slot)
+            else:
+                ids = index.ingest_sqlite(self.db_path, sql, total)
         except B2KError as e:
             index.close()
             if e.status != _capi.E_UNSUPPORTED:
@@ -254,6 +266,34 @@ class FAISSIndexBuilderDB:
             self._log(f"Native ingest declined ({e}); decoding in Python.", level="warning")
             return None, []
         return index, [int(i) for i in ids]
+
+    def _ingest_threads(self, rows=None, share=1):
+        """Reader threads of the native ingest.  `ingest_threads` (constructor) or B2K_INGEST_THREADS are taken as
+        given; the default is half the host cores (divided by `share` ranks), at most 8 — SQLite page reads and row
+        copies scale until the memory bus does not — and one thread per 50 000 rows at least: pinning the extra
+        staging slots costs more than a small database's whole ingest."""
+        n = getattr(self, "ingest_threads", None)
+        if n is None:
+            n = int(os.environ.get("B2K_INGEST_THREADS", "0")) or None
+        if n is None:
+            n = max(1, min(8, len(os.sched_getaffinity(0)) // (2 * max(1, share))))
+            if rows is not None:
+                n = max(1, min(n, int(rows) // 50_000))
+        return max(1, min(int(n), 16))
+
+    def _id_chunk_bounds(self, rows_per_chunk):
+        """Every rows_per_chunk-th image id (in id order) plus last id + 1: chunk c = ids in [b[c], b[c+1])."""
+        cur = self.read_cur
+        try:
+            firsts = [r[0] for r in cur.execute(
+                "SELECT id FROM (SELECT id, ROW_NUMBER() OVER (ORDER BY id) AS rn FROM images) "
+                f"WHERE (rn - 1) % {int(rows_per_chunk)} = 0 ORDER BY id")]
+        except sqlite3.OperationalError:          # SQLite < 3.25: no window functions
+            firsts = [r[0] for r in cur.execute("SELECT id FROM images ORDER BY id")][::int(rows_per_chunk)]
+        last = cur.execute("SELECT MAX(id) FROM images").fetchone()[0]
+        if not firsts or last is None:
+            return [0, 0]
+        return [int(x) for x in firsts] + [int(last) + 1]
 
     @staticmethod
     def _dist_world():
@@ -291,8 +331,13 @@ class FAISSIndexBuilderDB:
         # keyset page instead of LIMIT/OFFSET (which re-scans the r0 joined rows before the page on every rank):
         # the ids of the complete records, in order, give this rank's first and last id
         all_ids = [r[0] for r in self.read_cur.execute(f"SELECT i.id FROM images i {join_strs} ORDER BY i.id")]
+        mt_bounds = None
         if r1 > r0:
             sql = f"{base_sql} WHERE i.id BETWEEN {int(all_ids[r0])} AND {int(all_ids[r1 - 1])} ORDER BY i.id"
+            # reader threads of this rank (the host cores are shared by the ranks): chunks of 2048 complete records
+            threads = self._ingest_threads(r1 - r0, share=world)
+            if threads > 1:
+                mt_bounds = [int(x) for x in all_ids[r0:r1:2048]] + [int(all_ids[r1 - 1]) + 1]
         else:
             sql = f"{base_sql} WHERE 0"
         del all_ids
@@ -302,7 +347,11 @@ class FAISSIndexBuilderDB:
         ids = None
         if self.native_ingest and r1 > r0:
             try:
-                ids = [int(i) for i in index.ingest_sqlite(self.db_path, sql, r1 - r0)]
+                if mt_bounds is not None:
+                    sql_range = f"{base_sql} WHERE i.id >= ?1 AND i.id < ?2 ORDER BY i.id"
+                    ids = [int(i) for i in index.ingest_sqlite_mt(self.db_path, sql_range, mt_bounds, r1 - r0, threads, 2048)]
+                else:
+                    ids = [int(i) for i in index.ingest_sqlite(self.db_path, sql, r1 - r0)]
             except B2KError as e:
                 if e.status != _capi.E_UNSUPPORTED:
                     raise

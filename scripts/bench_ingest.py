@@ -41,6 +41,24 @@ for rep in range(2):
     res["native_loop"] = {"s": round(dt, 3), "rows_per_s": round(n / dt), "gb_per_s": round(n * 7872 / dt / 1e9, 2),
                           "stage_open_s": round(t_open, 3), "stage_close_s": round(t_close, 3)}
     ix.close()
+    # reader threads (b2k_ingest_sqlite_mt): own connection + two staging slots each, chunks committed in id order
+    sql_range = f"SELECT {sel} FROM images i {joins} WHERE i.id >= ?1 AND i.id < ?2 ORDER BY i.id"
+    bounds = b._id_chunk_bounds(2048)
+    res["native_threads"] = {}
+    for threads in (1, 2, 4, 8, 16):
+        ix = irb.FlatShard([48, 128, 1792], n, device=0)
+        bnd = np.ascontiguousarray(bounds, dtype=np.int64)
+        got = np.empty(n, np.int64); cnt = C.c_int64(0)
+        t0 = time.perf_counter(); check(_lib.b2k_stage_open_n(ix._h, 2048, 2 * threads)); t_open = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        check(_lib.b2k_ingest_sqlite_mt(ix._h, str(tmp / "images.db").encode(), sql_range.encode(), bnd.ctypes.data, bnd.size - 1,
+                                        threads, got.ctypes.data, n, C.byref(cnt)))
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter(); _lib.b2k_stage_close(ix._h); t_close = time.perf_counter() - t0
+        assert cnt.value == n and (got == ids[:n]).all()
+        res["native_threads"][str(threads)] = {"s": round(dt, 3), "rows_per_s": round(n / dt), "gb_per_s": round(n * 7872 / dt / 1e9, 2),
+                                               "stage_open_s": round(t_open, 3), "stage_close_s": round(t_close, 3)}
+        ix.close()
     ix = irb.FlatShard([48, 128, 1792], n, device=0)
     t0 = time.perf_counter()
     for batch in b._batch_records():

@@ -16,14 +16,15 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 tmp = Path(tempfile.gettempdir()) / "b2k_check_sharded_build"
 res = {"world": world}
 ok = True
-for case, foreign in (("clean", None), ("foreign_blob", ("sift", 4000))):
+for case, foreign in (("clean", None), ("foreign_blob", ("sift", 4000)), ("reader_threads", None)):
     if rank == 0:
         shutil.rmtree(tmp, ignore_errors=True); tmp.mkdir(parents=True)
         _make_db(tmp / "images.db", 6001, seed=7, foreign_at=foreign, missing={("sift", 9), ("color", 3000), ("dreamsim", 6001)})
     dist.barrier()
     types = ["color", "sift", "dreamsim"]
     b = FAISSIndexBuilderDB(db_path=str(tmp / "images.db"), vector_types=types, index_file=str(tmp / "sharded.faiss"),
-                            log_dir=str(tmp / f"logs{rank}"), batch_size=700, device=local)
+                            log_dir=str(tmp / f"logs{rank}"), batch_size=700, device=local,
+                            ingest_threads=3 if case == "reader_threads" else None)
     b._log = lambda m, level="info": None
     b.build_index()
     dist.barrier()

@@ -145,6 +145,56 @@ def test_native_ingest_small_slots_and_staging_reuse(tmp_path, gpu):
 
 
 @pytest.mark.gpu
+def test_native_ingest_reader_threads_equal_single_thread(tmp_path, gpu):
+    """b2k_ingest_sqlite_mt: 1, 3 and 8 reader threads over id chunks of 64 images (many more chunks than
+    threads, images with a missing part inside and at the edges of chunks) append exactly the rows, in exactly
+    the order, of the single-threaded loop; a foreign blob stops every thread with E_UNSUPPORTED; the capacity of
+    ids_out is enforced."""
+    import image_recommender_b200 as irb
+    from main.create_index import FAISSIndexBuilderDB
+    _make_db(tmp_path / "images.db", 1500, seed=4, missing={("sift", 1), ("color", 64), ("dreamsim", 65), ("sift", 1500)})
+    b = FAISSIndexBuilderDB(db_path=str(tmp_path / "images.db"), vector_types=["color", "sift", "dreamsim"],
+                            log_dir=str(tmp_path / "logs"))
+    sel, joins = b._make_select_and_joins()
+    sql = f"SELECT {sel} FROM images i {joins} ORDER BY i.id"
+    sql_range = f"SELECT {sel} FROM images i {joins} WHERE i.id >= ?1 AND i.id < ?2 ORDER BY i.id"
+    bounds = b._id_chunk_bounds(64)
+    assert bounds[0] == 1 and bounds[-1] == 1501 and len(bounds) == 25
+    ref = irb.FlatShard([48, 128, 1792], 1500, device=gpu)
+    ids_ref = ref.ingest_sqlite(tmp_path / "images.db", sql, 1500)
+    assert len(ids_ref) == 1496
+    for threads in (1, 3, 8):
+        a = irb.FlatShard([48, 128, 1792], 1500, device=gpu)
+        ids = a.ingest_sqlite_mt(tmp_path / "images.db", sql_range, bounds, 1500, threads, rows_per_slot=64)
+        assert ids.tolist() == ids_ref.tolist() and a.ntotal == ref.ntotal
+        for x, y in zip(a.get_rows(0, a.ntotal), ref.get_rows(0, ref.ntotal)):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+        a.reset()
+        with pytest.raises(irb.B2KError) as e:
+            a.ingest_sqlite_mt(tmp_path / "images.db", sql_range, bounds, 100, threads, rows_per_slot=64)
+        assert e.value.status == irb._capi.E_CAPACITY
+        a.close()
+    ref.close()
+    # the builder: an explicit thread count is taken as given, the default needs 50 000 rows per thread
+    assert b._ingest_threads(1500) == 1 and 1 <= b._ingest_threads(10_000_000) <= 8
+    b.ingest_threads = 4
+    assert b._ingest_threads(1500) == 4
+    b.read_conn.close(); b.write_conn.close()
+    f_mt, tab_mt, log_mt = _build(tmp_path, ["color", "sift", "dreamsim"], True, ingest_threads=3)
+    f_py, tab_py, _ = _build(tmp_path, ["color", "sift", "dreamsim"], False)
+    assert any("Native ingest: added" in m for m in log_mt) and tab_mt == tab_py and f_mt.read_bytes() == f_py.read_bytes()
+    _make_db(tmp_path / "foreign.db", 900, seed=5, foreign_at=("dreamsim", 700))
+    a = irb.FlatShard([48, 128, 1792], 900, device=gpu)
+    fb = FAISSIndexBuilderDB(db_path=str(tmp_path / "foreign.db"), vector_types=["color", "sift", "dreamsim"],
+                             log_dir=str(tmp_path / "logs"))
+    with pytest.raises(irb.B2KError) as e:
+        a.ingest_sqlite_mt(tmp_path / "foreign.db", sql_range, fb._id_chunk_bounds(64), 900, 4, rows_per_slot=64)
+    assert e.value.status == irb._capi.E_UNSUPPORTED and "image id 700" in str(e.value)
+    fb.read_conn.close(); fb.write_conn.close()
+    a.close()
+
+
+@pytest.mark.gpu
 def test_native_ingest_declines_foreign_blob_and_python_takes_over(tmp_path, gpu):
     """One tensor pickle in the middle of the table: the native loop stops with E_UNSUPPORTED, the
     builder rebuilds in Python (which decodes it as the reference does): same file either way."""
