@@ -63,6 +63,10 @@ def apply_config(args):
     if args.hnsw_rows < 0:
         cores = len(os.sched_getaffinity(0))
         args.hnsw_rows = min(c.get("hnsw_rows") or 50_000, 2500 * cores, c["rows"])
+    if args.sweep == "" and args.config == "3" and args.batch == 4096:
+        args.sweep = "8,32,128,160,256,512,1024,2048"
+    if args.sweep == "none":
+        args.sweep = ""
     if args.cpu_batch <= 0:
         args.cpu_batch = max(1, min(args.batch, 4096))
     args.workload_name = c["name"]
@@ -81,7 +85,9 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=None, help="total database rows over all ranks (default: the config's)")
     ap.add_argument("--batch", type=int, default=None, help="queries per step (default: the config's; 4096 for config 3)")
     ap.add_argument("--k", type=int, default=None, help="top-k (default 10; config 1: 5)")
-    ap.add_argument("--sweep", default="", help="comma-separated extra batch sizes reported under 'sweep'")
+    ap.add_argument("--sweep", default="", help="comma-separated extra batch sizes reported under 'sweep' (default for the "
+                                                "headline workload: 8,32,128,160,256,512,1024,2048 — BASELINE config 3 is a "
+                                                "query-batch sweep; 'none' turns it off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: NVLink peer-memory exchange kernels (default) or NCCL all-gather + merge")
