@@ -393,7 +393,11 @@ int search_pass(b2k_index* ix, const float* q_dev, int nq, int k, float* dist_de
   // tightening trades 2 x k latency-bound row gathers per query (25 us at batch 1) for ~3x fewer rows
   // to re-rank: a win once the re-rank is throughput-bound, a loss for the latency of small batches
   // (batch 128 at 10 M rows: tail 0.36 ms without, 0.15 ms with; batch 16: 0.11 ms either way)
-  const bool tighten = ix->opt_tighten > 1 || (ix->opt_tighten == 1 && nq >= 32);
+  // (with the fused cluster tail the cross-over moved up on short shards, where few rows sit within eps of the k-th
+  // score: 1.25 M rows, batch 32: tail 0.077 ms without, 0.103 with; batch 128: 0.105 vs 0.096; 10 M rows, batch 32:
+  // 0.220 vs 0.205; profiles/experiments/r02_exp_tighten.log)
+  const bool tighten = ix->opt_tighten > 1 ||
+                       (ix->opt_tighten == 1 && (nq >= 128 || (nq >= 32 && ix->ntotal >= 4000000)));
   se.db_f32 = tighten ? ix->f32 : nullptr; se.q = q_dev; se.D = ix->D;
   se.lb = w.lb; se.sat_count = w.fail_count + 1; se.sat_pairs = ix->opt_collect ? w.sat_pairs : nullptr;
   se.sat_cap = ix->opt_collect ? w.sat_cap : 0;

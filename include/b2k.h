@@ -48,7 +48,7 @@ typedef struct b2k_index b2k_index;
                                  /* tcgen05 path measured faster at every batch size and row width)      */
 #define B2K_OPT_SPLITS        5  /* 0 auto; else number of DB splits per query tile                      */
 #define B2K_OPT_TIGHTEN       8  /* candidate threshold from the exact scores of the k best rows: 1 auto (default: */
-                                 /* batches of 32 queries and more), 0 off, 2 always                           */
+                                 /* from 128 queries; from 32 on shards of 4 M rows and more), 0 off, 2 always */
 #define B2K_OPT_COLLECT       9  /* saturated partial lists are re-scanned by K-collect: 1 on (default), 0 = exhaustive scan */
 #define B2K_OPT_INLINE_SEED  10  /* <= 128 queries: seeding folded into the scoring launch (grid barrier): 1 on (default) */
 #define B2K_OPT_FUSED_TAIL   11  /* k <= 32: select + re-rank + finalize as ONE launch (cluster of CTAs per query), K-collect and  */
