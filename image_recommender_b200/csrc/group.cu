@@ -8,6 +8,8 @@
 // device's buffer over NVLink and the root merging them (K-exchange, xchg.cu).  Built purely on the public C
 // ABI (b2k_search_device, b2k_xchg_*, b2k_load): nothing here touches a shard's internals.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -62,6 +64,12 @@ struct b2k_group {
   uint64_t gen = 0;
   int pending = 0;
   bool stop = false;
+  // the same three, readable without the mutex: workers and the caller poll them for a short while before they
+  // sleep on the condition variables (a futex wake-up costs tens of microseconds per hand-off, twice per search:
+  // batch 1 on 8 GPUs 0.88 ms against 0.83 ms under torchrun)
+  std::atomic<uint64_t> gen_a{0};
+  std::atomic<int> pending_a{0};
+  std::atomic<bool> stop_a{false};
   std::function<int(int)> job;
   std::vector<int> status;
   std::vector<std::string> errs;
@@ -69,11 +77,26 @@ struct b2k_group {
 
 namespace {
 
+// Polls `done` for at most `us` microseconds (then the caller sleeps on its condition variable as before).
+constexpr int kSpinIdleUs = 200;       // a worker between two searches of a query stream
+constexpr int kSpinWaitUs = 3000;      // the caller while the devices work (a batch-1 search takes 0.8 .. 6 ms)
+template <typename F>
+void spin_until(F done, int us) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; !done(); ++i) {
+    if ((i & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(us)) return;
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 void worker(b2k_group* g, int rank) {
   cudaSetDevice(g->dev[rank].device);
   uint64_t seen = 0;
   for (;;) {
     std::function<int(int)> job;
+    spin_until([&] { return g->stop_a.load(std::memory_order_acquire) || g->gen_a.load(std::memory_order_acquire) != seen; }, kSpinIdleUs);
     {
       std::unique_lock<std::mutex> lk(g->mu);
       g->cv_go.wait(lk, [&] { return g->stop || g->gen != seen; });
@@ -87,6 +110,7 @@ void worker(b2k_group* g, int rank) {
       std::lock_guard<std::mutex> lk(g->mu);
       g->status[rank] = rc;
       g->errs[rank] = err;
+      g->pending_a.store(g->pending - 1, std::memory_order_release);
       if (--g->pending == 0) g->cv_done.notify_all();
     }
   }
@@ -98,9 +122,12 @@ int run_all(b2k_group* g, std::function<int(int)> job) {
     std::lock_guard<std::mutex> lk(g->mu);
     g->job = std::move(job);
     g->pending = g->n;
+    g->pending_a.store(g->n, std::memory_order_release);
     g->gen += 1;
+    g->gen_a.store(g->gen, std::memory_order_release);
   }
   g->cv_go.notify_all();
+  spin_until([&] { return g->pending_a.load(std::memory_order_acquire) == 0; }, kSpinWaitUs);
   std::unique_lock<std::mutex> lk(g->mu);
   g->cv_done.wait(lk, [&] { return g->pending == 0; });
   // every failing rank is named: the root's "peer did not publish" is usually the CONSEQUENCE of a peer's own error
@@ -264,6 +291,7 @@ void b2k_group_destroy(b2k_group* g) {
     {
       std::lock_guard<std::mutex> lk(g->mu);
       g->stop = true;
+      g->stop_a.store(true, std::memory_order_release);
     }
     g->cv_go.notify_all();
     for (std::thread& t : g->threads) t.join();
