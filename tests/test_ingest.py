@@ -263,3 +263,33 @@ def test_shard_ranges_partition_the_rows():
         assert max(sizes) == -(-n // world)
 
     run()
+
+
+def test_id_chunk_bounds_cover_sparse_ids(tmp_path):
+    """The reader threads' chunking (FAISSIndexBuilderDB._id_chunk_bounds): bounds are strictly increasing, every
+    chunk [b[c], b[c+1]) holds at most rows_per_chunk images, and together they hold every image exactly once — with
+    gaps in the ids (deleted images, AUTOINCREMENT jumps)."""
+    from main.create_index import FAISSIndexBuilderDB
+    rng = np.random.default_rng(3)
+    ids = np.unique(rng.integers(1, 10**7, size=5000)).tolist()
+    conn = sqlite3.connect(tmp_path / "images.db")
+    conn.executescript(DDL)
+    conn.executemany("INSERT INTO images (id, path) VALUES (?, ?)", [(i, f"p/{i}.jpg") for i in ids])
+    conn.commit()
+    conn.close()
+    b = FAISSIndexBuilderDB(db_path=str(tmp_path / "images.db"), vector_types=["color"], log_dir=str(tmp_path / "logs"))
+    for per in (1, 7, 64, 4096, 10**6):
+        bounds = b._id_chunk_bounds(per)
+        assert bounds[0] == ids[0] and bounds[-1] == ids[-1] + 1
+        assert all(x < y for x, y in zip(bounds, bounds[1:]))
+        arr = np.asarray(ids)
+        counts = [int(((arr >= lo) & (arr < hi)).sum()) for lo, hi in zip(bounds, bounds[1:])]
+        assert sum(counts) == len(ids) and max(counts) <= per and min(counts) >= 1
+    assert b._ingest_threads(10) == 1 and b._ingest_threads(10**7, share=8) >= 1
+    b.read_conn.close(); b.write_conn.close()
+    empty = sqlite3.connect(tmp_path / "empty.db")
+    empty.executescript(DDL)
+    empty.commit(); empty.close()
+    e = FAISSIndexBuilderDB(db_path=str(tmp_path / "empty.db"), vector_types=["color"], log_dir=str(tmp_path / "logs"))
+    assert e._id_chunk_bounds(64) == [0, 0]
+    e.read_conn.close(); e.write_conn.close()
