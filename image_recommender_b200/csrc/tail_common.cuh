@@ -67,6 +67,16 @@ __device__ __forceinline__ void block_topk_u64(const uint64_t* keys, int n, int 
   __shared__ uint64_t s_l;
   __shared__ unsigned int s_m;
   const int tid = threadIdx.x, T = blockDim.x;
+  if (n <= T) {                                   // one key per thread: rank it directly
+    const uint64_t mine = tid < n ? keys[tid] : 0ull;
+    if (tid < k) out[tid] = 0ull;
+    __syncthreads();
+    int rank = 0;
+    for (int e = 0; e < n; ++e) rank += keys[e] > mine ? 1 : 0;
+    if (mine != 0ull && rank < k) out[rank] = mine;
+    __syncthreads();
+    return;
+  }
   uint64_t cmax = 0ull;
   for (int e = tid; e < n; e += T) { const uint64_t v = keys[e]; cmax = v > cmax ? v : cmax; }
   wtop[tid] = cmax;

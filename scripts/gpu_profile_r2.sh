@@ -4,7 +4,7 @@
 #  queries), exchange push / merge (two ranks in one process)
 mkdir -p gpurun_out
 rm -f gpurun_out/prof_*.ncu-rep
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --hnsw-rows 0"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --hnsw-rows 0 --sweep none"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain bench failed"; tail -5 gpurun_out/plain.log; exit 1; }
 tail -1 gpurun_out/plain.log | cut -c1-300
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
