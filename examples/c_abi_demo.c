@@ -6,7 +6,8 @@
  * Builds a combo index (color 48 + sift 128 + dreamsim 1792) from host arrays the way
  * FAISSIndexBuilderDB hands batches to index.add (main/create_index.py:301-313), searches the way
  * ImageRecommender calls index.search (main/search_from_image.py:247), saves / reloads the index
- * (faiss.write_index / read_index) and checks every result against a brute-force loop in C.
+ * (faiss.write_index / read_index), searches it once more as a row-sharded group over every GPU of the box
+ * (b2k_group_*), and checks every result against a brute-force loop in C.
  * Prints "ok" and returns 0 when all of it agrees. */
 #include <math.h>
 #include <stdio.h>
@@ -98,6 +99,21 @@ int main(int argc, char** argv) {
   if (memcmp(lab, lab2, sizeof(int64_t) * (size_t)nq * k) || memcmp(dist, dist2, sizeof(float) * (size_t)nq * k)) {
     fprintf(stderr, "reloaded index answers differently\n");
     return 6;
+  }
+  /* the same file row-sharded over every GPU of the box, driven from this one thread (b2k_group_*; two ranks on
+   * device 0 when there is a single GPU): the same answers again */
+  {
+    const int32_t two_on_zero[2] = {0, 0};
+    b2k_group* grp = NULL;
+    CHECK(b2k_group_create(ndev >= 2 ? NULL : two_on_zero, ndev >= 2 ? ndev : 2, &grp));
+    CHECK(b2k_group_load(grp, path));
+    if (b2k_group_ntotal(grp) != n || b2k_group_dim(grp) != D) { fprintf(stderr, "group: wrong shape\n"); return 7; }
+    CHECK(b2k_group_search(grp, q, nq, k, dist2, lab2, NULL));
+    if (memcmp(lab, lab2, sizeof(int64_t) * (size_t)nq * k) || memcmp(dist, dist2, sizeof(float) * (size_t)nq * k)) {
+      fprintf(stderr, "the %d-shard group answers differently\n", (int)b2k_group_size(grp));
+      return 7;
+    }
+    b2k_group_destroy(grp);
   }
   b2k_stats st;
   CHECK(b2k_get_stats(ix, &st));

@@ -103,7 +103,8 @@ def test_header_is_plain_c_and_links(tmp_path):
 
 @pytest.mark.gpu
 def test_c_client_end_to_end(tmp_path):
-    """examples/c_abi_demo.c: add in two batches, search, brute-force check in C, save/load round trip."""
+    """examples/c_abi_demo.c: add in two batches, search, brute-force check in C, save/load round trip, the same file
+    as a row-sharded group (b2k_group_*) from the one C thread."""
     import os
     import subprocess
     exe, env = _build_c_demo(tmp_path)
