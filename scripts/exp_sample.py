@@ -23,6 +23,8 @@ if len(sys.argv) > 3 and sys.argv[3] == "tnshort":
              ([48, 128, 1792], 5_000_000, (130, 160, 192, 208))]
 if len(sys.argv) > 3 and sys.argv[3] == "small":
     cases = [([48, 128, 1792], 1_250_000, (16, 32, 64, 128, 256, 512)), ([48, 128, 1792], 10_000_000, (32, 128, 256, 512))]
+if len(sys.argv) > 3 and sys.argv[3] == "odd":
+    cases = [([48, 128, 1792], 10_000_000, (300, 384, 600, 640, 860, 896)), ([48, 128, 1792], 1_250_000, (384, 640, 896))]
 if len(sys.argv) > 3 and sys.argv[3] == "shards":
     cases = [([48, 128, 1792], 5_000_000, (512, 4096)), ([48, 128, 1792], 2_500_000, (512, 4096)), ([48, 128, 1792], 1_250_000, (512, 4096))]
 for dims, rows, batches in cases:
