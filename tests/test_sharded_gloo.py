@@ -66,3 +66,31 @@ def test_two_rank_gloo_matches_single_shard(tmp_path):
         assert np.array_equal(got["l"], wl)
         assert np.array_equal(got["ip"].view(np.uint32), wip.view(np.uint32))
         assert np.array_equal(got["d"].view(np.uint32), wd.view(np.uint32))
+
+
+def test_failed_local_search_publishes_its_epoch_before_raising():
+    """A rank whose local search raises still owes its peers an epoch: ShardedSearcher calls exchange.skip() (the
+    peers' merge kernels would otherwise wait out the 10 s timeout) and re-raises the original error."""
+    import torch
+    from image_recommender_b200.sharded import ShardedSearcher
+
+    class FakeExchange:
+        max_entries = 1 << 20
+        skipped = 0
+
+        def skip(self):
+            self.skipped += 1
+
+    def boom(q, k, out):
+        raise RuntimeError("local search failed")
+
+    ex = FakeExchange()
+    s = ShardedSearcher(boom, lambda ip, d, l: (d[0], l[0], ip[0]), exchange=ex)
+    s.world = 2                                  # as under torchrun with two ranks
+    with pytest.raises(RuntimeError, match="local search failed"):
+        s.search_device(torch.zeros((3, 8)), 5)
+    assert ex.skipped == 1
+    s.world = 1                                  # a single rank has nobody to tell
+    with pytest.raises(RuntimeError):
+        s.search_device(torch.zeros((3, 8)), 5)
+    assert ex.skipped == 1
